@@ -1,0 +1,960 @@
+// bsa_api.cu -- C ABI (include/bioshell_align.h) and host-side planning for the
+// B200 global-alignment kernels in gotoh_kernels.cuh.
+//
+// Host work here is what the reference does in `align_all_pairs`
+// (bioshell-seq/src/alignment/alignment_protocols.rs:83-115) around the aligner:
+// pick the pairs, encode the sequences (similarity_score.rs:125-134), collect the
+// results in t-major order.  There is no CPU alignment path in this file.
+#include "../../include/bioshell_align.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gotoh_kernels.cuh"
+#include "int_peak.cuh"
+
+using namespace bsa;
+
+namespace {
+
+constexpr int kMaxSets = 8;
+constexpr int kStreams = 4;
+constexpr int kMaxCodes = 128;
+constexpr size_t kSmemBudget = 200 * 1024;   // profile bytes per CTA we are willing to use
+constexpr int kKMax = 32;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct SeqSet {
+    bool loaded = false;
+    uint32_t n = 0;
+    uint64_t total = 0;
+    uint64_t maxlen = 0;
+    std::vector<uint64_t> off;       // host copy, n+1
+    std::vector<uint32_t> empties;   // indices of zero-length sequences (ascending)
+    DevBuf codes;                    // kFrontPad + total + kBackPad bytes
+    DevBuf doff;                     // n+1 uint64
+    SeqStoreDev dev() const {
+        SeqStoreDev d;
+        d.codes = codes.as<uint8_t>() + kFrontPad;
+        d.off = doff.as<uint64_t>();
+        d.n = n;
+        return d;
+    }
+    uint64_t len(uint32_t i) const { return off[i + 1] - off[i]; }
+};
+
+}  // namespace
+
+struct bsa_ctx {
+    int device = 0;
+    int sms = 0;
+    std::string err;
+    cudaStream_t streams[kStreams] = {};
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_s[kStreams] = {};
+
+    // residue alphabet: one code per distinct raw byte ever loaded
+    int code_of[256];
+    uint8_t byte_of[kMaxCodes];
+    int ncodes = 0;
+
+    bool have_scoring = false;
+    int32_t score[441];
+    uint8_t aaidx[256];
+    int go = 0, ge = 0;
+    int max_m = 0, min_m = 0;
+    int subst_codes = -1;          // alphabet size the device table was built for
+    DevBuf d_subst, d_isgap;
+
+    SeqSet sets[kMaxSets];
+
+    DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
+        raw, lut, presence;
+    bsa_stats stats;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(bsa_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+int fail_cuda(bsa_ctx* c, cudaError_t e, const char* what) {
+    cudaGetLastError();
+    return fail(c, e == cudaErrorMemoryAllocation ? BSA_ERR_OOM : BSA_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);      \
+    } while (0)
+
+inline int bitlen(uint64_t x) {
+    int b = 0;
+    while (x) { ++b; x >>= 1; }
+    return b;
+}
+
+// ---------------- kernel tables ----------------
+typedef void (*KernelFn)(const KArgs);
+KernelFn g_stream_single[kKMax + 1], g_stream_multi[kKMax + 1], g_dirs[kKMax + 1];
+size_t g_vec[kKMax + 1];
+
+template <int K>
+struct Reg {
+    static void run() {
+        g_stream_single[K] = gotoh_stream_kernel<K, false>;
+        g_stream_multi[K] = gotoh_stream_kernel<K, true>;
+        g_vec[K] = KTraits<K>::V;
+        Reg<K - 1>::run();
+    }
+};
+template <>
+struct Reg<0> {
+    static void run() {}
+};
+const int kDirsK[] = {2, 4, 8, 12, 16, 24, 32};
+void register_kernels() {
+    static bool done = false;
+    if (done) return;
+    Reg<kKMax>::run();
+    g_dirs[2] = gotoh_dirs_kernel<2>;
+    g_dirs[4] = gotoh_dirs_kernel<4>;
+    g_dirs[8] = gotoh_dirs_kernel<8>;
+    g_dirs[12] = gotoh_dirs_kernel<12>;
+    g_dirs[16] = gotoh_dirs_kernel<16>;
+    g_dirs[24] = gotoh_dirs_kernel<24>;
+    g_dirs[32] = gotoh_dirs_kernel<32>;
+    done = true;
+}
+size_t smem_for(int K, int C) { return (size_t)(C + 2) * g_vec[K] * 32 * sizeof(uint4); }
+
+// largest K whose profile fits the shared-memory budget for an alphabet of C codes
+int k_cap(int C) {
+    size_t vmax = kSmemBudget / ((size_t)(C + 2) * 32 * sizeof(uint4));
+    int kc = (int)std::min<size_t>(kKMax, vmax * 4);
+    return kc;
+}
+
+struct KChoice { int K; bool multi; uint32_t npass; };
+KChoice choose_k(uint64_t m, int C) {
+    const int kc = k_cap(C);
+    KChoice r;
+    if (m <= (uint64_t)32 * kc) {
+        r.K = (int)std::max<uint64_t>(1, (m + 31) / 32);
+        r.multi = false;
+        r.npass = 1;
+    } else {
+        r.npass = (uint32_t)((m + 32ull * kc - 1) / (32ull * kc));
+        r.K = (int)((m + 32ull * r.npass - 1) / (32ull * r.npass));
+        r.multi = true;
+    }
+    return r;
+}
+int choose_dirs_k(uint64_t m, int C) {
+    const int kc = k_cap(C);
+    int best = 0;
+    for (int k : kDirsK) {
+        if (k > kc) break;
+        best = k;
+        if ((uint64_t)32 * k >= m) return k;
+    }
+    return best;   // multi-pass with the largest K that fits
+}
+
+int launch(bsa_ctx* ctx, KernelFn fn, int K, const KArgs& a, cudaStream_t st) {
+    const size_t smem = smem_for(K, a.C);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, smem));
+    if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "kernel does not fit on an SM");
+    uint32_t grid = (uint32_t)std::min<uint64_t>(a.n_items, (uint64_t)nb * ctx->sms);
+    if (grid == 0) return BSA_OK;
+    fn<<<grid, kThreads, smem, st>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return BSA_OK;
+}
+
+// (re)build the C x C substitution table by residue code on the device
+int sync_scoring(bsa_ctx* ctx) {
+    if (!ctx->have_scoring) return fail(ctx, BSA_ERR_BAD_ARG, "bsa_set_scoring has not been called");
+    if (ctx->subst_codes == ctx->ncodes) return BSA_OK;
+    const int C = std::max(ctx->ncodes, 1);
+    std::vector<int16_t> tab((size_t)C * C);
+    std::vector<uint8_t> gap(C);
+    for (int a = 0; a < C; ++a) {
+        gap[a] = (ctx->byte_of[a] == '-' || ctx->byte_of[a] == '_') ? 1 : 0;   // msa.rs:264
+        for (int b = 0; b < C; ++b)
+            // similarity_score.rs:139-141 -> substitution_matrix.rs:81-83
+            tab[(size_t)a * C + b] =
+                (int16_t)ctx->score[ctx->aaidx[ctx->byte_of[a]] * 21 + ctx->aaidx[ctx->byte_of[b]]];
+    }
+    CK(ctx->d_subst.ensure(tab.size() * sizeof(int16_t)));
+    CK(ctx->d_isgap.ensure(gap.size()));
+    CK(cudaMemcpy(ctx->d_subst.p, tab.data(), tab.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_isgap.p, gap.data(), gap.size(), cudaMemcpyHostToDevice));
+    ctx->subst_codes = ctx->ncodes;
+    return BSA_OK;
+}
+
+struct PairReq { uint32_t q, t; uint64_t out; };
+
+// Fill + traceback through the direction-store kernels for an explicit pair list.
+// d_scores / d_nid are device arrays indexed by PairReq::out (either may be null).
+// If path_buf != null, pair i's path (right-aligned in its len_q+len_t slot at
+// slot_off[i]) and its length are returned on the host.
+int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<PairReq>& reqs,
+                   int32_t* d_scores, uint32_t* d_nid, uint8_t* path_buf,
+                   const std::vector<uint64_t>* slot_off, std::vector<uint32_t>* path_len,
+                   const std::vector<uint64_t>* req_index) {
+    if (reqs.empty()) return BSA_OK;
+    const int C = std::max(ctx->ncodes, 1);
+    // order by template so a CTA shares one profile between its warps
+    std::vector<uint32_t> order(reqs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](uint32_t a, uint32_t b) { return reqs[a].t < reqs[b].t; });
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t dir_budget = std::max<uint64_t>((uint64_t)(free_b * 0.6), 64ull << 20);
+
+    size_t pos = 0;
+    while (pos < order.size()) {
+        // ---- take a batch that fits the direction budget ----
+        std::vector<PairRec> recs;
+        std::vector<uint32_t> rec_req;
+        uint64_t dir_words = 0, scr_entries = 0, path_bytes = 0;
+        while (pos < order.size()) {
+            const PairReq& r = reqs[order[pos]];
+            const uint64_t n = Q.len(r.q), m = T.len(r.t);
+            const int K = choose_dirs_k(m, C);
+            if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
+            const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
+            const uint64_t words = npass * (n + 31) * 32 * W;
+            if (!recs.empty() && (dir_words + words) * 4 > dir_budget) break;
+            PairRec pr;
+            pr.q = r.q; pr.t = r.t; pr.out = r.out;
+            pr.dir_off = dir_words;
+            pr.scr_off = scr_entries;
+            pr.path_off = path_bytes;
+            pr.k = (uint32_t)K; pr.pad = 0;
+            dir_words += words;
+            scr_entries += npass > 1 ? n : 0;
+            path_bytes += n + m;
+            recs.push_back(pr);
+            rec_req.push_back(order[pos]);
+            ++pos;
+        }
+        // ---- items: (template, K) runs of the batch ----
+        std::vector<Item> items;
+        std::vector<int> item_k;
+        for (size_t i = 0; i < recs.size();) {
+            size_t j = i;
+            while (j < recs.size() && recs[j].t == recs[i].t) ++j;
+            // keep CTAs busy: at most 4 pairs per warp per item
+            for (size_t b = i; b < j; b += 4 * kWarpsPerCta) {
+                Item it;
+                it.t = recs[i].t;
+                it.q_begin = (uint32_t)b;
+                it.q_end = (uint32_t)std::min(j, b + 4 * kWarpsPerCta);
+                it.cshift = 0;
+                it.out_base = 0;
+                items.push_back(it);
+                item_k.push_back((int)recs[i].k);
+            }
+            i = j;
+        }
+        std::vector<size_t> perm(items.size());
+        for (size_t i = 0; i < perm.size(); ++i) perm[i] = i;
+        std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return item_k[a] > item_k[b]; });
+        std::vector<Item> sorted(items.size());
+        for (size_t i = 0; i < perm.size(); ++i) sorted[i] = items[perm[i]];
+
+        CK(ctx->pairs.ensure(recs.size() * sizeof(PairRec)));
+        CK(ctx->items.ensure(sorted.size() * sizeof(Item)));
+        CK(ctx->dirs.ensure(std::max<uint64_t>(dir_words, 1) * 4));
+        CK(ctx->scratch.ensure(std::max<uint64_t>(scr_entries, 1) * sizeof(uint2)));
+        CK(ctx->pstart.ensure(recs.size() * 4));
+        CK(ctx->status.ensure(4));
+        CK(ctx->counters.ensure(64 * 4));
+        if (path_buf) CK(ctx->path.ensure(std::max<uint64_t>(path_bytes, 1)));
+        cudaStream_t st = ctx->streams[0];
+        CK(cudaMemcpyAsync(ctx->pairs.p, recs.data(), recs.size() * sizeof(PairRec), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->items.p, sorted.data(), sorted.size() * sizeof(Item), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 64 * 4, st));
+        CK(cudaMemsetAsync(ctx->status.p, 0, 4, st));
+        ctx->stats.h2d_bytes += recs.size() * sizeof(PairRec) + sorted.size() * sizeof(Item);
+
+        size_t gi = 0;
+        int group = 0;
+        while (gi < sorted.size()) {
+            const int K = item_k[perm[gi]];
+            size_t gj = gi;
+            while (gj < sorted.size() && item_k[perm[gj]] == K) ++gj;
+            KArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Q = Q.dev(); a.T = T.dev();
+            a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+            a.items = ctx->items.as<Item>() + gi;
+            a.n_items = (uint32_t)(gj - gi);
+            a.item_counter = ctx->counters.as<uint32_t>() + group;
+            a.scores = d_scores; a.nident = nullptr;
+            a.scratch = ctx->scratch.as<uint2>(); a.scratch_stride = 0;
+            a.pairs = ctx->pairs.as<PairRec>();
+            a.dirs = ctx->dirs.as<uint32_t>();
+            int rc = launch(ctx, g_dirs[K], K, a, st);
+            if (rc) return rc;
+            gi = gj;
+            ++group;
+        }
+        TraceArgs ta;
+        ta.Q = Q.dev(); ta.T = T.dev();
+        ta.pairs = ctx->pairs.as<PairRec>();
+        ta.n_pairs = (uint32_t)recs.size();
+        ta.dirs = ctx->dirs.as<uint32_t>();
+        ta.isgap = ctx->d_isgap.as<uint8_t>();
+        ta.path = path_buf ? ctx->path.as<uint8_t>() : nullptr;
+        ta.path_start = ctx->pstart.as<uint32_t>();
+        ta.nident = d_nid;
+        ta.status = ctx->status.as<uint32_t>();
+        traceback_kernel<<<(ta.n_pairs + 63) / 64, 64, 0, st>>>(ta);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+        uint32_t status = 0;
+        CK(cudaMemcpyAsync(&status, ctx->status.p, 4, cudaMemcpyDeviceToHost, st));
+        std::vector<uint32_t> starts;
+        std::vector<uint8_t> hpath;
+        if (path_buf) {
+            starts.resize(recs.size());
+            hpath.resize(path_bytes);
+            CK(cudaMemcpyAsync(starts.data(), ctx->pstart.p, recs.size() * 4, cudaMemcpyDeviceToHost, st));
+            if (path_bytes)
+                CK(cudaMemcpyAsync(hpath.data(), ctx->path.p, path_bytes, cudaMemcpyDeviceToHost, st));
+            ctx->stats.d2h_bytes += recs.size() * 4 + path_bytes;
+        }
+        CK(cudaStreamSynchronize(st));
+        if (status) return fail(ctx, BSA_ERR_CUDA, "traceback met an invalid direction code");
+        if (path_buf) {
+            for (size_t i = 0; i < recs.size(); ++i) {
+                const uint64_t ri = (*req_index)[rec_req[i]];
+                const uint64_t slot = Q.len(recs[i].q) + T.len(recs[i].t);
+                const uint32_t s0 = starts[i];
+                memcpy(path_buf + (*slot_off)[ri] + s0, hpath.data() + recs[i].path_off + s0, slot - s0);
+                (*path_len)[ri] = (uint32_t)(slot - s0);
+            }
+        }
+    }
+    return BSA_OK;
+}
+
+}  // namespace
+
+// =====================================================================
+//                               C ABI
+// =====================================================================
+extern "C" {
+
+int bsa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+bsa_ctx* bsa_create(int device_id) {
+    int n = bsa_device_count();
+    if (n <= 0) { fail(nullptr, BSA_ERR_CUDA, "no CUDA device is visible (there is no CPU fallback)"); return nullptr; }
+    if (device_id < 0 || device_id >= n) { fail(nullptr, BSA_ERR_BAD_ARG, "device_id out of range"); return nullptr; }
+    if (cudaSetDevice(device_id) != cudaSuccess) { fail(nullptr, BSA_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { fail(nullptr, BSA_ERR_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major != 10) {
+        fail(nullptr, BSA_ERR_CUDA, "device is not sm_100 (this library carries sm_100a code only)");
+        return nullptr;
+    }
+    bsa_ctx* c = new (std::nothrow) bsa_ctx();
+    if (!c) return nullptr;
+    c->device = device_id;
+    c->sms = prop.multiProcessorCount;
+    for (int i = 0; i < 256; ++i) c->code_of[i] = -1;
+    memset(&c->stats, 0, sizeof(c->stats));
+    for (int i = 0; i < kStreams; ++i) {
+        cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_s[i], cudaEventDisableTiming);
+    }
+    cudaEventCreate(&c->ev_start);
+    cudaEventCreate(&c->ev_end);
+    register_kernels();
+    if (cudaGetLastError() != cudaSuccess) { delete c; fail(nullptr, BSA_ERR_CUDA, "stream/event creation failed"); return nullptr; }
+    return c;
+}
+
+void bsa_destroy(bsa_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
+    DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
+                      &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
+                      &c->presence, &c->d_subst, &c->d_isgap};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < kStreams; ++i) {
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->ev_s[i]) cudaEventDestroy(c->ev_s[i]);
+    }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    delete c;
+}
+
+const char* bsa_last_error(const bsa_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+// substitution_matrix.rs:96-135
+int bsa_parse_ncbi_matrix(const char* text, size_t len, int32_t score[441], uint8_t aa_index[256]) {
+    if (!text || !score || !aa_index) return BSA_ERR_BAD_ARG;
+    std::fill(score, score + 441, 0);
+    std::fill(aa_index, aa_index + 256, (uint8_t)0);
+    size_t row = 0, at = 0;
+    while (at < len && row < 20) {
+        size_t eol = at;
+        while (eol < len && text[eol] != '\n') ++eol;
+        std::string line(text + at, eol - at);
+        at = eol + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty() && (line[0] == '#' || line[0] == ' ')) continue;   // :105
+        std::vector<std::string> tok;
+        size_t k = 0;
+        while (k < line.size()) {
+            while (k < line.size() && isspace((unsigned char)line[k])) ++k;
+            size_t s = k;
+            while (k < line.size() && !isspace((unsigned char)line[k])) ++k;
+            if (k > s) tok.emplace_back(line, s, k - s);
+        }
+        if (tok.size() < 23) return BSA_ERR_FORMAT;                           // :108
+        auto to_i32 = [](const std::string& s, int32_t* out) {
+            size_t i = 0;
+            bool neg = false;
+            if (!s.empty() && (s[0] == '+' || s[0] == '-')) { neg = s[0] == '-'; i = 1; }
+            if (i >= s.size()) return false;
+            long long v = 0;
+            for (; i < s.size(); ++i) {
+                if (s[i] < '0' || s[i] > '9') return false;
+                v = v * 10 + (s[i] - '0');
+                if (v > 2147483648LL) return false;
+            }
+            v = neg ? -v : v;
+            if (v > 2147483647LL) return false;
+            *out = (int32_t)v;
+            return true;
+        };
+        const unsigned char letter = (unsigned char)tok[0][0];
+        if (letter == 255) return BSA_ERR_FORMAT;
+        aa_index[letter] = (uint8_t)row;                                      // :110
+        for (size_t j = 1; j <= 20; ++j) {                                    // :112-119
+            int32_t v;
+            if (!to_i32(tok[j], &v)) return BSA_ERR_FORMAT;
+            score[row * 21 + (j - 1)] = v;
+            score[(j - 1) * 21 + row] = v;
+        }
+        int32_t vx;                                                           // :121-126
+        if (!to_i32(tok[tok.size() - 2], &vx)) return BSA_ERR_FORMAT;
+        score[row * 21 + 20] = vx;
+        score[20 * 21 + row] = vx;
+        ++row;
+    }
+    aa_index[(unsigned char)'X'] = 20;                                        // :130
+    score[20 * 21 + 20] = -1;                                                 // :132
+    return BSA_OK;
+}
+
+int bsa_set_scoring(bsa_ctx* ctx, const int32_t score[441], const uint8_t aa_index[256],
+                    int32_t gap_open, int32_t gap_extend) {
+    if (!ctx || !score || !aa_index) return fail(ctx, BSA_ERR_BAD_ARG, "null argument");
+    // outside this domain the reference's sentinel can tie or its backtrace underflows
+    // (SURVEY.md 8a note 1); the kernels drop the sentinel, so refuse.
+    if (!(gap_open <= gap_extend && gap_extend <= 0 && gap_open < 0))
+        return fail(ctx, BSA_ERR_UNSUPPORTED_GAPS, "need gap_open <= gap_extend <= 0 and gap_open < 0");
+    int mx = -1000000, mn = 1000000;
+    for (int i = 0; i < 441; ++i) {
+        if (score[i] > 32000 || score[i] < -32000) return fail(ctx, BSA_ERR_RANGE, "substitution score out of int16 range");
+        mx = std::max(mx, score[i]);
+        mn = std::min(mn, score[i]);
+    }
+    for (int i = 0; i < 256; ++i)
+        if (aa_index[i] > 20) return fail(ctx, BSA_ERR_BAD_ARG, "aa_index entry > 20");
+    memcpy(ctx->score, score, sizeof(ctx->score));
+    memcpy(ctx->aaidx, aa_index, 256);
+    ctx->go = gap_open;
+    ctx->ge = gap_extend;
+    ctx->max_m = mx;
+    ctx->min_m = mn;
+    ctx->have_scoring = true;
+    ctx->subst_codes = -1;
+    return BSA_OK;
+}
+
+int bsa_load_sequences(bsa_ctx* ctx, int set_id, const uint8_t* residues_raw, const uint64_t* offsets,
+                       uint32_t n) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    if (set_id < 0 || set_id >= kMaxSets || !offsets) return fail(ctx, BSA_ERR_BAD_ARG, "bad set_id or null offsets");
+    if (n == 0) return fail(ctx, BSA_ERR_EMPTY, "empty sequence set");
+    for (uint32_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, BSA_ERR_BAD_ARG, "offsets must be non-decreasing");
+    const uint64_t base = offsets[0], total = offsets[n] - base;
+    if (total && !residues_raw) return fail(ctx, BSA_ERR_BAD_ARG, "null residues");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->streams[0];
+    SeqSet& S = ctx->sets[set_id];
+    S.loaded = false;
+    S.n = n;
+    S.total = total;
+    S.off.resize((size_t)n + 1);
+    S.maxlen = 0;
+    S.empties.clear();
+    for (uint32_t i = 0; i <= n; ++i) S.off[i] = offsets[i] - base;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t l = S.off[i + 1] - S.off[i];
+        S.maxlen = std::max(S.maxlen, l);
+        if (l == 0) S.empties.push_back(i);
+    }
+    const size_t buf_bytes = kFrontPad + total + kBackPad;
+    CK(S.codes.ensure(buf_bytes));
+    CK(S.doff.ensure(((size_t)n + 1) * 8));
+    CK(ctx->raw.ensure(total + 16));
+    CK(ctx->lut.ensure(256));
+    CK(ctx->presence.ensure(32));
+    CK(cudaMemcpyAsync(S.doff.p, S.off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) CK(cudaMemcpyAsync(ctx->raw.p, residues_raw + base, total, cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes += ((size_t)n + 1) * 8 + total;
+    // which byte values occur?  (new ones get a residue code)
+    CK(cudaMemsetAsync(ctx->presence.p, 0, 32, st));
+    if (total) {
+        const int blocks = (int)std::min<uint64_t>((total + 256 * 64 - 1) / (256 * 64), (uint64_t)ctx->sms * 8);
+        byte_presence_kernel<<<blocks, 256, 0, st>>>(ctx->raw.as<uint8_t>(), total, ctx->presence.as<uint32_t>());
+        CK(cudaGetLastError());
+    }
+    uint32_t pres[8];
+    CK(cudaMemcpyAsync(pres, ctx->presence.p, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (pres[7] >> 31) return fail(ctx, BSA_ERR_ALPHABET, "residue byte 255 (the reference's [u8;255] lookup panics)");
+    for (int b = 0; b < 255; ++b) {
+        if (!((pres[b >> 5] >> (b & 31)) & 1u) || ctx->code_of[b] >= 0) continue;
+        if (ctx->ncodes >= kMaxCodes) return fail(ctx, BSA_ERR_ALPHABET, "more than 128 distinct residue byte values");
+        ctx->code_of[b] = ctx->ncodes;
+        ctx->byte_of[ctx->ncodes++] = (uint8_t)b;
+    }
+    uint8_t lut[256];
+    for (int b = 0; b < 256; ++b) lut[b] = (uint8_t)(ctx->code_of[b] < 0 ? 0 : ctx->code_of[b]);
+    CK(cudaMemcpyAsync(ctx->lut.p, lut, 256, cudaMemcpyHostToDevice, st));
+    // pads: zeros, with the byte just before sequence 0 flagged so every lane starts clean
+    CK(cudaMemsetAsync(S.codes.p, 0, kFrontPad, st));
+    CK(cudaMemsetAsync(S.codes.as<uint8_t>() + kFrontPad - 1, (int)kLastFlag, 1, st));
+    CK(cudaMemsetAsync(S.codes.as<uint8_t>() + kFrontPad + total, 0, kBackPad, st));
+    if (total) {
+        const int blocks = (int)std::min<uint64_t>((total / 16 + 255) / 256 + 1, (uint64_t)ctx->sms * 16);
+        encode_kernel<<<blocks, 256, 0, st>>>(ctx->raw.as<uint8_t>(), S.codes.as<uint8_t>() + kFrontPad, total,
+                                             ctx->lut.as<uint8_t>());
+        CK(cudaGetLastError());
+        mark_last_kernel<<<(n + 255) / 256, 256, 0, st>>>(S.codes.as<uint8_t>() + kFrontPad, S.doff.as<uint64_t>(), n);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));
+    S.loaded = true;
+    return BSA_OK;
+}
+
+int bsa_plan_shards(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_counts, uint32_t n_shards,
+                    uint32_t* bounds) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets || !bounds || n_shards == 0)
+        return fail(ctx, BSA_ERR_BAD_ARG, "bad argument");
+    const SeqSet &Q = ctx->sets[q_set], &T = ctx->sets[t_set];
+    if (!Q.loaded || !T.loaded) return fail(ctx, BSA_ERR_BAD_ARG, "sequence set not loaded");
+    std::vector<double> pre((size_t)T.n + 1, 0.0);
+    for (uint32_t t = 0; t < T.n; ++t) {
+        const uint32_t cnt = q_counts ? std::min(q_counts[t], Q.n) : Q.n;
+        pre[t + 1] = pre[t] + (double)T.len(t) * (double)Q.off[cnt];
+    }
+    bounds[0] = 0;
+    for (uint32_t r = 1; r < n_shards; ++r) {
+        const double want = pre[T.n] * r / n_shards;
+        bounds[r] = (uint32_t)(std::lower_bound(pre.begin(), pre.end(), want) - pre.begin());
+        bounds[r] = std::max(bounds[r], bounds[r - 1]);
+        bounds[r] = std::min(bounds[r], T.n);
+    }
+    bounds[n_shards] = T.n;
+    return BSA_OK;
+}
+
+int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_counts, uint32_t t_begin,
+                        uint32_t t_end, uint32_t flags, int32_t* scores, uint32_t* n_identical,
+                        uint64_t* n_results) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    const auto wall0 = std::chrono::steady_clock::now();
+    if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets)
+        return fail(ctx, BSA_ERR_BAD_ARG, "bad set id");
+    const SeqSet &Q = ctx->sets[q_set], &T = ctx->sets[t_set];
+    if (!Q.loaded || !T.loaded) return fail(ctx, BSA_ERR_EMPTY, "sequence set not loaded");
+    if (t_begin > t_end || t_end > T.n) return fail(ctx, BSA_ERR_BAD_ARG, "bad template range");
+    CK(cudaSetDevice(ctx->device));
+    int rc = sync_scoring(ctx);
+    if (rc) return rc;
+    const bool want_s = (flags & BSA_WANT_SCORE) && scores;
+    const bool want_i = (flags & BSA_WANT_IDENTICAL) && n_identical;
+    const bool out_dev = (flags & BSA_OUT_DEVICE) != 0;
+    const int C = std::max(ctx->ncodes, 1);
+    const uint64_t h2d0 = ctx->stats.h2d_bytes;   // loads since the last call count toward it
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.h2d_bytes = h2d0;
+
+    // ---------------- plan ----------------
+    std::vector<uint64_t> first((size_t)(t_end - t_begin) + 1, 0);
+    double total_cells = 0.0;
+    for (uint32_t t = t_begin; t < t_end; ++t) {
+        const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
+        if (cnt > Q.n) return fail(ctx, BSA_ERR_BAD_ARG, "q_counts entry exceeds the query set size");
+        first[t - t_begin + 1] = first[t - t_begin] + cnt;
+        total_cells += (double)T.len(t) * (double)Q.off[cnt];
+    }
+    const uint64_t n_res = first.back();
+    if (n_results) *n_results = n_res;
+    ctx->stats.pairs = n_res;
+    ctx->stats.cells = (uint64_t)total_cells;
+    if (n_res == 0) return BSA_OK;
+
+    const double target_cells = std::min(std::max(total_cells / 60000.0, 1048576.0), 268435456.0);
+    struct Group { std::vector<Item> items; };
+    std::vector<Group> groups(2 * (kKMax + 1));
+    std::vector<Fix> fixes;
+    std::vector<PairReq> fallback;
+    uint64_t scratch_stride = 0;
+    double padded = 0.0;
+    const int cs_cap = bitlen(Q.maxlen);
+
+    for (uint32_t t = t_begin; t < t_end; ++t) {
+        const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
+        if (cnt == 0) continue;
+        const uint64_t m = T.len(t);
+        const uint64_t kbase = first[t - t_begin];
+        if (m == 0) {
+            // empty template: the reference returns the row-0 border value... for an empty
+            // query against it the loop never runs: H[0]=0 (global.rs:76,143); otherwise
+            // the left border go + (n-1) ge after n rows (global.rs:99,140).
+            for (uint32_t q = 0; q < cnt; ++q) {
+                const uint64_t n = Q.len(q);
+                fixes.push_back(Fix{kbase + q, n == 0 ? 0 : (int32_t)(ctx->go + (int64_t)(n - 1) * ctx->ge), 0u});
+            }
+            continue;
+        }
+        const KChoice kc = choose_k(m, C);
+        if (kc.K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
+        // integer-field check: score << (cs+2) must stay inside int32 for every cell
+        const int cs = std::min(bitlen(m), cs_cap);
+        const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
+        const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
+        const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
+                           (int64_t)std::max(-ctx->min_m, 0);
+        const bool fits = std::max(ub, lb) + 8 < lim;
+        const uint64_t m_pad = 32ull * kc.K * kc.npass;
+        uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
+        if (kc.multi) xb = std::min<uint64_t>(xb, (uint64_t)kWarpsPerCta * 16384);
+
+        // runs of non-empty queries inside [0, cnt)
+        auto e_it = Q.empties.begin();
+        uint32_t run_b = 0;
+        while (run_b < cnt) {
+            while (e_it != Q.empties.end() && *e_it < run_b) ++e_it;
+            uint32_t run_e = cnt;
+            if (e_it != Q.empties.end() && *e_it < cnt) run_e = *e_it;
+            if (run_e == run_b) {
+                // empty query: the top border value go + (m-1) ge (global.rs:81-88,143)
+                fixes.push_back(Fix{kbase + run_b, (int32_t)(ctx->go + (int64_t)(m - 1) * ctx->ge), 0u});
+                ++run_b;
+                continue;
+            }
+            if (!fits) {
+                for (uint32_t q = run_b; q < run_e; ++q) fallback.push_back(PairReq{q, t, kbase + q});
+            } else {
+                uint32_t q = run_b;
+                while (q < run_e) {
+                    const uint64_t lim_off = Q.off[q] + xb;
+                    uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + run_e + 1, lim_off) -
+                                             Q.off.begin()) - 1;
+                    q2 = std::max(q2, q + 1);
+                    q2 = std::min(q2, run_e);
+                    Item it;
+                    it.t = t; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cs;
+                    it.out_base = kbase + q;
+                    groups[kc.K + (kc.multi ? kKMax + 1 : 0)].items.push_back(it);
+                    const uint64_t x = Q.off[q2] - Q.off[q];
+                    padded += (double)(x + 31 * kWarpsPerCta) * (double)m_pad;
+                    if (kc.multi) scratch_stride = std::max(scratch_stride, x / kWarpsPerCta + Q.maxlen + 64);
+                    q = q2;
+                }
+            }
+            run_b = run_e;
+        }
+    }
+    ctx->stats.padded_cells = (uint64_t)padded;
+    ctx->stats.fallback_pairs = (uint32_t)std::min<size_t>(fallback.size(), 0xffffffffu);
+
+    // ---------------- outputs ----------------
+    int32_t* d_scores = nullptr;
+    uint32_t* d_nid = nullptr;
+    if (out_dev) {
+        d_scores = want_s ? scores : nullptr;
+        d_nid = want_i ? n_identical : nullptr;
+    } else {
+        if (want_s) { CK(ctx->out_scores.ensure(n_res * 4)); d_scores = ctx->out_scores.as<int32_t>(); }
+        if (want_i) { CK(ctx->out_nid.ensure(n_res * 4)); d_nid = ctx->out_nid.as<uint32_t>(); }
+    }
+
+    // ---------------- upload the plan, launch ----------------
+    size_t n_items = 0;
+    int n_groups = 0;
+    for (auto& g : groups) { n_items += g.items.size(); n_groups += g.items.empty() ? 0 : 1; }
+    ctx->stats.items = (uint32_t)n_items;
+    CK(ctx->counters.ensure(groups.size() * 4));
+    cudaStream_t s0 = ctx->streams[0];
+    if (n_items) {
+        std::vector<Item> all;
+        all.reserve(n_items);
+        std::vector<size_t> goff(groups.size(), 0);
+        // long templates (large K) first: they are the expensive items
+        std::vector<int> gorder;
+        for (int g = (int)groups.size() - 1; g >= 0; --g) if (!groups[g].items.empty()) gorder.push_back(g);
+        std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) {
+            return (a % (kKMax + 1)) * (a > kKMax ? 64 : 1) > (b % (kKMax + 1)) * (b > kKMax ? 64 : 1);
+        });
+        for (int g : gorder) { goff[g] = all.size(); all.insert(all.end(), groups[g].items.begin(), groups[g].items.end()); }
+        CK(ctx->items.ensure(all.size() * sizeof(Item)));
+        CK(cudaMemcpyAsync(ctx->items.p, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice, s0));
+        ctx->stats.h2d_bytes += all.size() * sizeof(Item);
+        CK(cudaMemsetAsync(ctx->counters.p, 0, groups.size() * 4, s0));
+        if (scratch_stride) {
+            // every resident warp of a MULTI kernel owns one slice
+            const size_t warps = (size_t)ctx->sms * 8 * kWarpsPerCta;
+            CK(ctx->scratch.ensure(warps * scratch_stride * sizeof(uint2)));
+        }
+        CK(cudaEventRecord(ctx->ev_start, s0));
+        for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+        int li = 0;
+        for (int g : gorder) {
+            const bool multi = g > kKMax;
+            const int K = multi ? g - (kKMax + 1) : g;
+            KArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Q = Q.dev(); a.T = T.dev();
+            a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+            a.items = ctx->items.as<Item>() + goff[g];
+            a.n_items = (uint32_t)groups[g].items.size();
+            a.item_counter = ctx->counters.as<uint32_t>() + g;
+            a.scores = d_scores; a.nident = d_nid;
+            a.scratch = ctx->scratch.as<uint2>(); a.scratch_stride = (uint32_t)scratch_stride;
+            rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, ctx->streams[li % kStreams]);
+            if (rc) return rc;
+            ++li;
+        }
+        for (int i = 1; i < kStreams; ++i) {
+            CK(cudaEventRecord(ctx->ev_s[i], ctx->streams[i]));
+            CK(cudaStreamWaitEvent(s0, ctx->ev_s[i], 0));
+        }
+    } else {
+        CK(cudaEventRecord(ctx->ev_start, s0));
+    }
+    // pairs whose score range does not fit the packed lanes: direction-store path
+    if (!fallback.empty()) {
+        rc = run_pairs_dirs(ctx, Q, T, fallback, d_scores, d_nid, nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    if (!fixes.empty() && (d_scores || d_nid)) {
+        CK(ctx->fixes.ensure(fixes.size() * sizeof(Fix)));
+        CK(cudaMemcpyAsync(ctx->fixes.p, fixes.data(), fixes.size() * sizeof(Fix), cudaMemcpyHostToDevice, s0));
+        apply_fix_kernel<<<(uint32_t)((fixes.size() + 255) / 256), 256, 0, s0>>>(
+            ctx->fixes.as<Fix>(), (uint32_t)fixes.size(), d_scores, d_nid);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+    }
+    CK(cudaEventRecord(ctx->ev_end, s0));
+    if (!out_dev) {
+        if (want_s) CK(cudaMemcpyAsync(scores, d_scores, n_res * 4, cudaMemcpyDeviceToHost, s0));
+        if (want_i) CK(cudaMemcpyAsync(n_identical, d_nid, n_res * 4, cudaMemcpyDeviceToHost, s0));
+        ctx->stats.d2h_bytes += (want_s ? n_res * 4 : 0) + (want_i ? n_res * 4 : 0);
+    }
+    CK(cudaStreamSynchronize(s0));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));
+    ctx->stats.kernel_ms = ms;
+    ctx->stats.total_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return BSA_OK;
+}
+
+int bsa_all_vs_all(bsa_ctx* ctx, int set_id, uint32_t flags, int32_t* scores, uint32_t* n_identical) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    if (set_id < 0 || set_id >= kMaxSets || !ctx->sets[set_id].loaded)
+        return fail(ctx, BSA_ERR_EMPTY, "sequence set not loaded");
+    const uint32_t n = ctx->sets[set_id].n;
+    std::vector<uint32_t> counts(n);
+    for (uint32_t t = 0; t < n; ++t) counts[t] = t;   // q < t: alignment_protocols.rs:96-97
+    return bsa_align_all_pairs(ctx, set_id, set_id, counts.data(), 0, n, flags, scores, n_identical, nullptr);
+}
+
+int bsa_one_vs_many(bsa_ctx* ctx, int q_set, int db_set, uint32_t flags, int32_t* scores,
+                    uint32_t* n_identical) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    if (db_set < 0 || db_set >= kMaxSets || !ctx->sets[db_set].loaded)
+        return fail(ctx, BSA_ERR_EMPTY, "sequence set not loaded");
+    return bsa_align_all_pairs(ctx, q_set, db_set, nullptr, 0, ctx->sets[db_set].n, flags, scores,
+                               n_identical, nullptr);
+}
+
+int bsa_align_pairs_paths(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_idx, const uint32_t* t_idx,
+                          uint64_t n_pairs, int32_t* scores, uint32_t* n_identical, uint8_t* path_buf,
+                          uint64_t* path_off) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    const auto wall0 = std::chrono::steady_clock::now();
+    if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets)
+        return fail(ctx, BSA_ERR_BAD_ARG, "bad set id");
+    const SeqSet &Q = ctx->sets[q_set], &T = ctx->sets[t_set];
+    if (!Q.loaded || !T.loaded) return fail(ctx, BSA_ERR_EMPTY, "sequence set not loaded");
+    if (n_pairs && (!q_idx || !t_idx)) return fail(ctx, BSA_ERR_BAD_ARG, "null pair list");
+    if (path_buf && !path_off) return fail(ctx, BSA_ERR_BAD_ARG, "path_buf needs path_off");
+    CK(cudaSetDevice(ctx->device));
+    int rc = sync_scoring(ctx);
+    if (rc) return rc;
+    const uint64_t h2d0 = ctx->stats.h2d_bytes;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.h2d_bytes = h2d0;
+    ctx->stats.pairs = n_pairs;
+    if (path_off) path_off[0] = 0;
+    if (n_pairs == 0) return BSA_OK;
+
+    std::vector<PairReq> reqs;
+    std::vector<uint64_t> req_index;          // request -> original pair index
+    std::vector<uint64_t> slot_off(n_pairs + 1, 0);
+    std::vector<uint32_t> plen(n_pairs, 0);
+    std::vector<int32_t> h_scores(n_pairs, 0);
+    std::vector<uint32_t> h_nid(n_pairs, 0);
+    std::vector<uint8_t> degenerate(n_pairs, 0);
+    double cells = 0;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        if (q_idx[p] >= Q.n || t_idx[p] >= T.n) return fail(ctx, BSA_ERR_BAD_ARG, "pair index out of range");
+        const uint64_t n = Q.len(q_idx[p]), m = T.len(t_idx[p]);
+        slot_off[p + 1] = slot_off[p] + n + m;
+        cells += (double)n * (double)m;
+        if (n == 0 || m == 0) {
+            // only a border is walked: all '-' (row 0) or all '|' (column 0)
+            degenerate[p] = 1;
+            h_scores[p] = (n == 0 && m == 0) ? 0 : (int32_t)(ctx->go + (int64_t)(n + m - 1) * ctx->ge);
+            plen[p] = (uint32_t)(n + m);
+        } else {
+            reqs.push_back(PairReq{q_idx[p], t_idx[p], p});
+            req_index.push_back(p);
+        }
+    }
+    ctx->stats.cells = (uint64_t)cells;
+    CK(ctx->out_scores.ensure(n_pairs * 4));
+    CK(ctx->out_nid.ensure(n_pairs * 4));
+    cudaStream_t s0 = ctx->streams[0];
+    CK(cudaMemsetAsync(ctx->out_scores.p, 0, n_pairs * 4, s0));
+    CK(cudaMemsetAsync(ctx->out_nid.p, 0, n_pairs * 4, s0));
+    CK(cudaEventRecord(ctx->ev_start, s0));
+    rc = run_pairs_dirs(ctx, Q, T, reqs, ctx->out_scores.as<int32_t>(), ctx->out_nid.as<uint32_t>(), path_buf,
+                        &slot_off, &plen, &req_index);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_end, s0));
+    std::vector<int32_t> ds(n_pairs);
+    std::vector<uint32_t> dn(n_pairs);
+    CK(cudaMemcpyAsync(ds.data(), ctx->out_scores.p, n_pairs * 4, cudaMemcpyDeviceToHost, s0));
+    CK(cudaMemcpyAsync(dn.data(), ctx->out_nid.p, n_pairs * 4, cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    ctx->stats.d2h_bytes += n_pairs * 8;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        if (!degenerate[p]) { h_scores[p] = ds[p]; h_nid[p] = dn[p]; }
+        if (scores) scores[p] = h_scores[p];
+        if (n_identical) n_identical[p] = h_nid[p];
+    }
+    if (path_buf) {
+        // compact the right-aligned slots into back-to-back paths, in pair order
+        uint64_t w = 0;
+        for (uint64_t p = 0; p < n_pairs; ++p) {
+            const uint64_t slot = slot_off[p + 1] - slot_off[p];
+            if (degenerate[p]) {
+                const uint64_t m = T.len(t_idx[p]);
+                memset(path_buf + w, m ? '-' : '|', plen[p]);   // tmp space: w <= slot_off[p]
+            } else {
+                memmove(path_buf + w, path_buf + slot_off[p] + (slot - plen[p]), plen[p]);
+            }
+            w += plen[p];
+            path_off[p + 1] = w;
+        }
+    } else if (path_off) {
+        for (uint64_t p = 0; p < n_pairs; ++p) path_off[p + 1] = 0;
+    }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));
+    ctx->stats.kernel_ms = ms;
+    ctx->stats.total_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return BSA_OK;
+}
+
+void* bsa_host_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void bsa_host_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int bsa_get_stats(const bsa_ctx* ctx, bsa_stats* out) {
+    if (!ctx || !out) return BSA_ERR_BAD_ARG;
+    *out = ctx->stats;
+    return BSA_OK;
+}
+
+int bsa_measure_int_peak(bsa_ctx* ctx, int which, double* lane_ops_per_s, double* sm_clock_mhz) {
+    if (!ctx || !lane_ops_per_s) return BSA_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    double ops = 0, mhz = 0;
+    cudaError_t e = bsa::measure_int_peak(which, ctx->sms, ctx->streams[0], &ops, &mhz);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "int-peak microbenchmark");
+    *lane_ops_per_s = ops;
+    if (sm_clock_mhz) *sm_clock_mhz = mhz;
+    return BSA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,569 @@
+// gotoh_kernels.cuh -- hand-written sm_100a kernels for Needleman-Wunsch/Gotoh global
+// alignment with the BioShell reference's exact tie-breaking.
+//
+// Replaces (reference paths relative to the BioShell checkout):
+//   GlobalAligner::align      bioshell-seq/src/alignment/global.rs:57-145
+//   GlobalAligner::backtrace  bioshell-seq/src/alignment/global.rs:146-201
+//   identity count            bioshell-seq/src/msa/msa.rs:261-269
+//
+// Design (DESIGN.md has the long version):
+//  * TEMPLATE-STATIONARY, QUERY-STREAMING systolic warp.  A CTA owns one template
+//    (the DP columns).  Lane l of a warp keeps K consecutive columns in registers;
+//    the residues of MANY queries are streamed through the lanes back to back
+//    (lane l works on stream position s-l at step s), so the pipeline fill/drain
+//    of the 32-lane wavefront is paid once per work item, not once per pair.
+//    Column boundaries (H and the eagerly-computed E) hop lanes by warp shuffle.
+//  * ONE 32-bit lane carries (score, tie-priority, identical-count) packed as
+//        v = score << (cs+2) | prio << cs | count          (cs = count bits)
+//    so that a signed integer max IS the reference's selection rule:
+//    higher score first, then the reference's priority among equal scores
+//    (H: diagonal 3 > E 2 > F 1, global.rs:161-169; E/F: extend beats open,
+//    global.rs:109,122), and the count of identical residues of the winning
+//    path rides along for free.  The whole cell is 8 integer instructions:
+//        e  = eraw | PH                      LOP3
+//        f  = fraw[c] | PV                   LOP3
+//        d  = hdiag + T[q][t]                IADD3      (T carries prio 3 and the identity bit)
+//        h  = max3(d, e, f)                  VIMNMX3    (DPX)
+//        hc = h & ~prio                      LOP3
+//        hg = hc + GO                        IADD3
+//        eraw    = max(e + GE, hg)           VIADDMNMX  (DPX)
+//        fraw[c] = max(f + GE, hg)           VIADDMNMX  (DPX)
+//    The reference's third E/F term (e_from_f / f_from_e) and its capacity
+//    dependent sentinel never win for gap_open <= gap_extend <= 0 (SURVEY.md 8a
+//    note 1), so they are dropped; the borders are produced eagerly instead.
+//  * The substitution scores come from a per-template PROFILE in shared memory,
+//    laid out [code][vec][lane] as uint4 so that every lane reads its own 16-byte
+//    bank group: conflict-free LDS.128 whatever residue each lane is on.
+//  * DIRS variant: the same recurrences with cs = 0; the priority bits that fall
+//    out of the max ARE the traceback directions, so each cell also emits a 4-bit
+//    code (2-bit H source + E-extended + F-extended) to HBM, written coalesced in
+//    step-major order, and a second kernel walks them (global.rs:146-201).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bsa {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr uint32_t kLastFlag = 0x80u;  // set on the last residue of every sequence in the store
+constexpr uint32_t kCodeMask = 0x7Fu;
+constexpr int kFrontPad = 64;          // bytes before the first sequence (last one flagged)
+constexpr int kBackPad = 128;          // bytes after the last sequence
+
+// One unit of work: template t against the contiguous query range [q_begin, q_end).
+struct Item {
+    uint32_t t;
+    uint32_t q_begin;
+    uint32_t q_end;
+    uint32_t cshift;    // count-field width for this item (0 in DIRS mode)
+    uint64_t out_base;  // result index of pair (q_begin, t)
+};
+
+// DIRS mode: one pair per entry; pairs of one item share the template.
+struct PairRec {
+    uint32_t q, t;
+    uint64_t out;       // result index (scores / n_identical / path slot)
+    uint64_t dir_off;   // word offset of this pair's direction planes
+    uint64_t scr_off;   // entry offset of this pair's boundary column (multi-pass templates)
+    uint64_t path_off;  // byte offset of this pair's path slot (len_q + len_t bytes)
+    uint32_t k;         // columns per lane the fill kernel used
+    uint32_t pad;
+};
+
+struct SeqStoreDev {
+    const uint8_t* codes;   // points at the first residue of sequence 0 (pads around it)
+    const uint64_t* off;    // n+1 offsets
+    uint32_t n;
+};
+
+struct KArgs {
+    SeqStoreDev Q, T;
+    const int16_t* subst;   // C x C substitution scores by residue code
+    const uint8_t* isgap;   // C flags: code is '-' or '_' (never identical, msa.rs:264)
+    int C;
+    int go, ge;
+    const Item* items;
+    uint32_t n_items;
+    uint32_t* item_counter;
+    int32_t* scores;        // may be null
+    uint32_t* nident;       // may be null
+    uint2* scratch;         // MULTI: per-warp boundary columns
+    uint32_t scratch_stride;  // entries per warp
+    const PairRec* pairs;   // DIRS
+    uint32_t* dirs;         // DIRS
+};
+
+__device__ __forceinline__ int max3_s32(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+__device__ __forceinline__ int addmax_s32(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
+
+struct Consts {
+    int GE, GO, MASK, PH, PV, T_PAD;
+    int hb0;  // packed H[1][0] = gap_open
+    int cs;
+};
+
+template <int K>
+struct KTraits {
+    static constexpr int V = (K + 3) / 4;        // uint4 vectors per lane per profile row
+    static constexpr int W = (K + 7) / 8;        // direction words per lane per step
+    static constexpr int ROW = V * 32;           // uint4 per profile row
+};
+
+// Shared-memory layout (uint4 units): profile rows [C][V][32], then rsH [V][32], rsF [V][32].
+template <int K>
+__host__ __device__ constexpr size_t smem_bytes(int C) {
+    return (size_t)(C + 2) * KTraits<K>::ROW * sizeof(uint4);
+}
+
+// Build the profile of template columns [colbase, colbase + 32K) and the per-lane
+// top-border reset vectors.  All threads of the CTA participate.
+template <int K>
+__device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rsF,
+                                              const uint8_t* __restrict__ tc, uint32_t m,
+                                              uint32_t colbase, const KArgs& a, const Consts& cs) {
+    constexpr int V = KTraits<K>::V;
+    constexpr int ROW = KTraits<K>::ROW;
+    const int C = a.C;
+    const int S = 1 << (cs.cs + 2);
+    const int P3 = 3 << cs.cs;
+    for (int idx = threadIdx.x; idx < C * ROW; idx += blockDim.x) {
+        const int code = idx / ROW;
+        const int r = idx - code * ROW;
+        const int v = r >> 5, lane = r & 31;
+        const bool gap = a.isgap[code] != 0;
+        int o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = 4 * v + e;
+            const uint32_t col = colbase + lane * K + c;
+            int val = cs.T_PAD;
+            if (c < K && col < m) {
+                const int tcode = tc[col] & kCodeMask;
+                val = (int)a.subst[code * C + tcode] * S + P3 +
+                      ((cs.cs > 0 && tcode == code && !gap) ? 1 : 0);   // no count field when cs == 0
+            }
+            o[e] = val;
+        }
+        prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    // top border: H[0][j] = go + (j-1) ge  (global.rs:81-88); eager F for row 1 =
+    // H[0][j] + go (opened, never extended from the sentinel: global.rs:118-128)
+    for (int r = threadIdx.x; r < ROW; r += blockDim.x) {
+        const int v = r >> 5, lane = r & 31;
+        int h[4], f[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = 4 * v + e;
+            const long long j = (long long)colbase + lane * K + c + 1;  // DP column
+            const int hv = (int)((a.go + (j - 1) * a.ge) * S);
+            h[e] = hv;
+            f[e] = hv + cs.GO;
+        }
+        rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
+        rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict__ src) {
+    constexpr int V = KTraits<K>::V;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const uint4 x = src[v * 32];
+        if (4 * v + 0 < K) dst[4 * v + 0] = (int)x.x;
+        if (4 * v + 1 < K) dst[4 * v + 1] = (int)x.y;
+        if (4 * v + 2 < K) dst[4 * v + 2] = (int)x.z;
+        if (4 * v + 3 < K) dst[4 * v + 3] = (int)x.w;
+    }
+}
+
+// Stream the residues codes[g0 .. g1) (whole sequences, back to back, last residue
+// of each flagged) through the 32 lanes for ONE column block of the template.
+//   FIRST: this block starts at template column 0 (left border is generated),
+//          otherwise lane 0 reads the boundary column from `scratch`.
+//   LASTP: this block holds the template's last column (results are emitted),
+//          otherwise lane 31 writes the boundary column to `scratch`.
+template <int K, bool DIRS, bool MULTI>
+__device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
+                                             uint64_t g1, const uint4* prof, const uint4* rsH,
+                                             const uint4* rsF, const int lane, const bool first,
+                                             const bool lastp, const int lane_last,
+                                             const int slot_last, const int hdiag0,
+                                             const Consts cs, uint2* __restrict__ scratch,
+                                             int32_t* __restrict__ scores,
+                                             uint32_t* __restrict__ nident, uint64_t out_idx0,
+                                             uint32_t* __restrict__ dirs) {
+    constexpr int V = KTraits<K>::V;
+    constexpr int W = KTraits<K>::W;
+    constexpr int ROW = KTraits<K>::ROW;
+    const uint32_t X = (uint32_t)(g1 - g0);
+    const int span = (MULTI && !lastp) ? 31 : lane_last;
+    const uint32_t nsteps = X + (uint32_t)span;
+
+    int Hc[K], Fr[K], T[K];
+    load_vec<K>(Hc, rsH + lane);
+    load_vec<K>(Fr, rsF + lane);
+    int hdiag = hdiag0;
+    int hb = cs.hb0;
+    int oh = 0, oe = 0;
+    uint32_t emitted = 0;
+
+    const uint8_t* p = codes + g0 - lane;   // lane's position at step 0 (may sit in the padding)
+    uint32_t b = *p;
+    uint2 sc_next = make_uint2(0u, 0u);
+    if (MULTI && !first && lane == 0 && X > 0) sc_next = scratch[0];
+
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        const uint32_t bn = p[1];
+        ++p;
+        const uint4* row = prof + (b & kCodeMask) * ROW + lane;
+        load_vec<K>(T, row);
+
+        int hin = __shfl_up_sync(0xffffffffu, oh, 1);
+        int er = __shfl_up_sync(0xffffffffu, oe, 1);
+        if (lane == 0) {
+            if (!MULTI || first) {
+                // left border: H[i][0] = go + (i-1) ge ; E[i][1] opens from it (global.rs:96-101)
+                hin = hb;
+                er = hb + cs.GO;
+            } else {
+                hin = (int)sc_next.x;
+                er = (int)sc_next.y;
+            }
+        }
+        if (MULTI && !first && lane == 0 && s + 1 < X) sc_next = scratch[s + 1];
+        hb += cs.GE;
+
+        int hd = hdiag;
+        hdiag = hin;
+        uint32_t dw[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) dw[w] = 0u;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+            const int e = er | cs.PH;
+            const int f = Fr[c] | cs.PV;
+            const int d = hd + T[c];
+            const int h = max3_s32(d, e, f);
+            if (DIRS) {
+                const uint32_t nib = ((uint32_t)h & 3u) | ((((uint32_t)er | (uint32_t)Fr[c]) & 3u) << 2);
+                dw[c >> 3] = (dw[c >> 3] << 4) | nib;
+            }
+            const int hc = h & cs.MASK;
+            const int hg = hc + cs.GO;
+            er = addmax_s32(e, cs.GE, hg);
+            Fr[c] = addmax_s32(f, cs.GE, hg);
+            hd = Hc[c];
+            Hc[c] = hc;
+        }
+        oh = Hc[K - 1];
+        oe = er;
+
+        if (DIRS) {
+            uint32_t* dp = dirs + ((size_t)s * 32 + lane) * W;
+#pragma unroll
+            for (int w = 0; w < W; ++w) dp[w] = dw[w];
+        }
+        if (MULTI && !lastp && lane == 31) {
+            const uint32_t pos = s - 31u;     // wraps for s < 31 -> fails the bound test
+            if (pos < X) scratch[pos] = make_uint2((uint32_t)oh, (uint32_t)oe);
+        }
+
+        if (b & kLastFlag) {
+            // end of a query: emit H[n][m] from the lane that owns column m, then put the
+            // lane back on the top border for the next query of the stream.
+            const uint32_t pos = s - (uint32_t)lane;
+            const bool valid = pos < X;
+            if (lastp && valid && lane == lane_last) {
+                int v = 0;
+#pragma unroll
+                for (int c = 0; c < K; ++c)
+                    if (c == slot_last) v = Hc[c];
+                const uint64_t k = out_idx0 + emitted;
+                if (scores) scores[k] = v >> (cs.cs + 2);
+                if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);
+            }
+            emitted += valid ? 1u : 0u;
+            load_vec<K>(Hc, rsH + lane);
+            load_vec<K>(Fr, rsF + lane);
+            hdiag = hdiag0;
+            hb = cs.hb0;
+        }
+        b = bn;
+    }
+}
+
+__device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
+                                                    uint32_t hi, uint64_t x) {
+    // first index i in [lo, hi] with off[i] >= x
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (off[mid] >= x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+template <int K>
+__device__ __forceinline__ Consts make_consts(int go, int ge, int cshift) {
+    Consts cs;
+    cs.cs = cshift;
+    const int S = 1 << (cshift + 2);
+    cs.GE = ge * S;
+    cs.GO = go * S;
+    cs.MASK = ~(3 << cshift);
+    cs.PH = 2 << cshift;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
+    cs.PV = 1 << cshift;   // F: vertical, gap in the template
+    cs.T_PAD = 3 << cshift;
+    cs.hb0 = go * S;
+    return cs;
+}
+
+// Score + identity for (template, query range) items.  Persistent CTAs pull items from
+// an atomic counter; the CTA's warps split the item's residue stream evenly.
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kThreads) gotoh_stream_kernel(const KArgs a) {
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_item;
+    constexpr int ROW = KTraits<K>::ROW;
+    uint4* prof = smem;
+    uint4* rsH = smem + (size_t)a.C * ROW;
+    uint4* rsF = rsH + ROW;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t ii = s_item;
+        if (ii >= a.n_items) break;
+        const Item it = a.items[ii];
+        const uint64_t t0 = a.T.off[it.t];
+        const uint32_t m = (uint32_t)(a.T.off[it.t + 1] - t0);
+        const uint8_t* tc = a.T.codes + t0;
+        const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift);
+
+        // this warp's share of the item's residue stream (whole queries)
+        const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
+        const uint64_t span = x1 - x0;
+        const uint32_t qa = warp == 0 ? it.q_begin
+                                      : lower_bound_off(a.Q.off, it.q_begin, it.q_end,
+                                                        x0 + span * warp / kWarpsPerCta);
+        const uint32_t qb = warp == kWarpsPerCta - 1
+                                ? it.q_end
+                                : lower_bound_off(a.Q.off, it.q_begin, it.q_end,
+                                                  x0 + span * (warp + 1) / kWarpsPerCta);
+        const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+        const uint32_t npass = MULTI ? (m + 32 * K - 1) / (32 * K) : 1u;
+        uint2* scratch = MULTI ? a.scratch + (size_t)(blockIdx.x * kWarpsPerCta + warp) * a.scratch_stride
+                               : nullptr;
+
+        for (uint32_t pass = 0; pass < npass; ++pass) {
+            const uint32_t colbase = pass * 32 * K;
+            __syncthreads();   // previous profile is no longer read by anyone
+            build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
+            __syncthreads();
+            const bool lastp = (pass + 1 == npass);
+            const int lane_last = (int)((m - 1 - colbase) / K);
+            const int slot_last = (int)((m - 1 - colbase) % K);
+            const long long jl = (long long)colbase + (long long)lane * K;  // DP column left of the lane
+            const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * (1 << (cs.cs + 2)));
+            if (g1 > g0)
+                stream_block<K, false, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
+                                              lastp, lastp ? lane_last : 31, slot_last, hdiag0, cs,
+                                              scratch, a.scores, a.nident,
+                                              it.out_base + (qa - it.q_begin), nullptr);
+            if (MULTI) __syncwarp();
+        }
+    }
+}
+
+// Direction-store variant: items are (template, pair range); each warp takes whole
+// pairs.  cshift = 0, so the packed value is score*4 + prio and n_identical comes
+// from the traceback kernel instead.
+template <int K>
+__global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_item;
+    constexpr int ROW = KTraits<K>::ROW;
+    constexpr int W = KTraits<K>::W;
+    uint4* prof = smem;
+    uint4* rsH = smem + (size_t)a.C * ROW;
+    uint4* rsF = rsH + ROW;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t ii = s_item;
+        if (ii >= a.n_items) break;
+        const Item it = a.items[ii];   // q_begin/q_end index a.pairs here
+        const uint64_t t0 = a.T.off[it.t];
+        const uint32_t m = (uint32_t)(a.T.off[it.t + 1] - t0);
+        const uint8_t* tc = a.T.codes + t0;
+        const Consts cs = make_consts<K>(a.go, a.ge, 0);
+        const uint32_t npass = (m + 32 * K - 1) / (32 * K);
+
+        for (uint32_t pass = 0; pass < npass; ++pass) {
+            const uint32_t colbase = pass * 32 * K;
+            __syncthreads();
+            build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
+            __syncthreads();
+            const bool lastp = (pass + 1 == npass);
+            const int lane_last = (int)((m - 1 - colbase) / K);
+            const int slot_last = (int)((m - 1 - colbase) % K);
+            const long long jl = (long long)colbase + (long long)lane * K;
+            const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * 4);
+            for (uint32_t pi = it.q_begin + warp; pi < it.q_end; pi += kWarpsPerCta) {
+                const PairRec pr = a.pairs[pi];
+                const uint64_t g0 = a.Q.off[pr.q], g1 = a.Q.off[pr.q + 1];
+                const uint32_t n = (uint32_t)(g1 - g0);
+                // plane of this pass: (n + 31) steps x 32 lanes x W words
+                uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 31) * 32 * W;
+                // the boundary column must survive until this pair's next pass (passes are
+                // the outer loop because the CTA shares the profile), so it is per pair
+                stream_block<K, true, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
+                                            lastp, lastp ? lane_last : 31, slot_last, hdiag0, cs,
+                                            a.scratch + pr.scr_off, a.scores, nullptr, pr.out, dirs);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+
+// Walks the stored directions exactly as GlobalAligner::backtrace does
+// (global.rs:146-201): state H follows diag > E > F, state E/F keeps going while the
+// cell it leaves was an extension.  One thread per pair; writes the path glyphs
+// backwards into the pair's slot and counts identical residues on the way
+// (raw-byte equality == code equality; '-'/'_' never count, msa.rs:264).
+struct TraceArgs {
+    SeqStoreDev Q, T;
+    const PairRec* pairs;
+    uint32_t n_pairs;
+    const uint32_t* dirs;
+    const uint8_t* isgap;
+    uint8_t* path;          // may be null (identity only)
+    uint32_t* path_start;   // per pair (by position in `pairs`): first byte of the path in its slot
+    uint32_t* nident;       // indexed by PairRec::out, may be null
+    uint32_t* status;       // set to 1 if an invalid direction is met
+};
+
+__global__ void traceback_kernel(const TraceArgs a) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_pairs) return;
+    const PairRec pr = a.pairs[p];
+    const uint8_t* qc = a.Q.codes + a.Q.off[pr.q];
+    const uint8_t* tc = a.T.codes + a.T.off[pr.t];
+    const uint32_t n = (uint32_t)(a.Q.off[pr.q + 1] - a.Q.off[pr.q]);
+    const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - a.T.off[pr.t]);
+    const uint32_t K = pr.k, W = (K + 7) / 8, BK = 32 * K;
+    const size_t plane = (size_t)(n + 31) * 32 * W;
+    const uint32_t* dirs = a.dirs + pr.dir_off;
+    uint8_t* out = a.path ? a.path + pr.path_off : nullptr;
+    uint32_t pos = n + m, i = n, j = m, nid = 0;
+    int st = 0;
+    while (i > 0 && j > 0) {
+        const uint32_t col = j - 1, pass = col / BK, lc = col - pass * BK;
+        const uint32_t lane = lc / K, c = lc - lane * K;
+        const uint32_t step = (i - 1) + lane, w = c >> 3;
+        const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
+        const uint32_t sh = 4 * (cnt - 1 - (c & 7));
+        const uint32_t nib = (dirs[pass * plane + ((size_t)step * 32 + lane) * W + w] >> sh) & 15u;
+        if (st == 0) {
+            const uint32_t hd = nib & 3u;
+            if (hd == 3u) {
+                --pos;
+                if (out) out[pos] = '*';
+                const uint32_t x = qc[i - 1] & kCodeMask, y = tc[j - 1] & kCodeMask;
+                nid += (x == y && !a.isgap[x]) ? 1u : 0u;
+                --i; --j;
+            } else if (hd == 2u) st = 1;
+            else if (hd == 1u) st = 2;
+            else { *a.status = 1u; break; }
+        } else if (st == 1) {
+            --pos;
+            if (out) out[pos] = '-';
+            --j;
+            st = (nib & 8u) ? 1 : 0;
+        } else {
+            --pos;
+            if (out) out[pos] = '|';
+            --i;
+            st = (nib & 4u) ? 2 : 0;
+        }
+    }
+    // borders: row 0 is all E-extensions, column 0 all F-extensions (global.rs:81-88,96-97)
+    while (j > 0) { --pos; if (out) out[pos] = '-'; --j; }
+    while (i > 0) { --pos; if (out) out[pos] = '|'; --i; }
+    a.path_start[p] = pos;
+    if (a.nident) a.nident[pr.out] = nid;
+}
+
+// ---- sequence-store construction (K0) ----
+// presence[8]: 256-bit mask of byte values that occur
+__global__ void byte_presence_kernel(const uint8_t* __restrict__ raw, uint64_t total,
+                                     uint32_t* __restrict__ presence) {
+    __shared__ uint32_t sm[8];
+    if (threadIdx.x < 8) sm[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t b = raw[i];
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+            if ((b >> 5) == (uint32_t)w) loc[w] |= 1u << (b & 31);
+    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (loc[w]) atomicOr(&sm[w], loc[w]);
+    __syncthreads();
+    if (threadIdx.x < 8 && sm[threadIdx.x]) atomicOr(&presence[threadIdx.x], sm[threadIdx.x]);
+}
+
+// raw bytes -> residue codes through a 256-entry LUT (similarity_score.rs:125-134 encodes
+// per pair; here it happens once per set), 16 bytes per thread where aligned.
+__global__ void encode_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ codes,
+                              uint64_t total, const uint8_t* __restrict__ lut_g) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x & 255] = lut_g[threadIdx.x & 255];
+    __syncthreads();
+    const uint64_t nvec = total / 16;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint4* rv = reinterpret_cast<const uint4*>(raw);
+    uint4* cv = reinterpret_cast<uint4*>(codes);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 x = rv[i];
+        uint32_t* w = reinterpret_cast<uint32_t*>(&x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = w[k];
+            w[k] = (uint32_t)lut[v & 255] | ((uint32_t)lut[(v >> 8) & 255] << 8) |
+                   ((uint32_t)lut[(v >> 16) & 255] << 16) | ((uint32_t)lut[v >> 24] << 24);
+        }
+        cv[i] = x;
+    }
+    for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += stride)
+        codes[i] = lut[raw[i]];
+}
+
+__global__ void mark_last_kernel(uint8_t* __restrict__ codes, const uint64_t* __restrict__ off,
+                                 uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && off[i + 1] > off[i]) codes[off[i + 1] - 1] |= (uint8_t)kLastFlag;
+}
+
+// writes a few (index, score, n_identical) triples computed on the host (empty sequences)
+struct Fix { uint64_t k; int32_t score; uint32_t nid; };
+__global__ void apply_fix_kernel(const Fix* __restrict__ fx, uint32_t n, int32_t* scores,
+                                 uint32_t* nident) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (scores) scores[fx[i].k] = fx[i].score;
+    if (nident) nident[fx[i].k] = fx[i].nid;
+}
+
+}  // namespace bsa

@@ -1,0 +1,175 @@
+/*
+ * bioshell_align.h -- C ABI of libbioshell_align.so, the B200-native (sm_100a)
+ * drop-in for the ONE data-parallel hot path of dgront/BioShell v4: all-vs-all /
+ * one-vs-many pairwise global alignment (Needleman-Wunsch, Gotoh affine gaps,
+ * BLOSUM/PAM matrices) with the reference aligner's exact tie-breaking.
+ *
+ * The reference has no FFI at all (100 % Rust); these entry points
+ * are what a `bioshell-seq` `extern "C"` block would bind.  Each one names the
+ * reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   bsa_parse_ncbi_matrix  SubstitutionMatrix::ncbi_matrix_from_buffer
+ *                          bioshell-seq/src/scoring/substitution_matrix.rs:96-135
+ *   bsa_set_scoring        SequenceSimilarityScore::new + the gap arguments of
+ *                          align_all_pairs (scoring/similarity_score.rs:67-71,
+ *                          alignment/alignment_protocols.rs:83-84)
+ *   bsa_load_sequences     the `&Vec<Sequence>` arguments of align_all_pairs and the
+ *                          per-pair byte->index encode, similarity_score.rs:125-134
+ *   bsa_align_all_pairs    align_all_pairs' t-major double loop around
+ *                          GlobalAligner::align + backtrace + the identity count of
+ *                          the reporter: alignment_protocols.rs:94-110,
+ *                          global.rs:57-201, msa.rs:261-269
+ *   bsa_all_vs_all         the `if_triangle_only = true` call of
+ *                          bin/cluster_sequences.rs:175-176
+ *   bsa_one_vs_many        the `if_triangle_only = false` call of
+ *                          bioshell-seq/examples/needleman_wunsh.rs:108-109
+ *   bsa_align_pairs_paths  GlobalAligner::align + backtrace -> AlignmentPath
+ *                          (global.rs:57-201, alignment_path.rs:34-48,107-115)
+ *
+ * Conventions: plain pointers and sizes only.  The caller allocates every input
+ * and output buffer and keeps it alive for the duration of the call; the library
+ * owns device memory and streams inside bsa_ctx and never retains caller pointers
+ * after return.  Calls are synchronous (results complete on return).  A bsa_ctx is
+ * bound to ONE CUDA device and used by one host thread at a time; use one context
+ * (one process) per GPU and shard by template range for multi-GPU.  There is NO CPU
+ * fallback: without a usable CUDA device every compute entry point returns
+ * BSA_ERR_CUDA.  No C++ exception crosses this boundary.
+ */
+#ifndef BIOSHELL_ALIGN_H
+#define BIOSHELL_ALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSA_VERSION 1
+
+/* return codes */
+#define BSA_OK 0
+#define BSA_ERR_BAD_ARG (-1)
+#define BSA_ERR_UNSUPPORTED_GAPS (-2) /* need gap_open <= gap_extend <= 0 and gap_open < 0 */
+#define BSA_ERR_RANGE (-3)            /* score range does not fit the kernel's integer fields */
+#define BSA_ERR_CUDA (-4)
+#define BSA_ERR_OOM (-5)
+#define BSA_ERR_FORMAT (-6)           /* NCBI matrix text: IncorrectNCBIFormat / CantParseNCBIEntry */
+#define BSA_ERR_ALPHABET (-7)         /* > 128 distinct residue byte values, or byte 255 (reference panics) */
+#define BSA_ERR_EMPTY (-8)            /* empty sequence set (reference: max().unwrap() panics) */
+
+/* flags for the alignment entry points */
+#define BSA_WANT_SCORE 1u
+#define BSA_WANT_IDENTICAL 2u
+#define BSA_OUT_DEVICE 4u /* output pointers are device pointers on the context's GPU */
+
+typedef struct bsa_ctx bsa_ctx;
+
+/* Number of CUDA devices visible to this process (0 when there is none). */
+int bsa_device_count(void);
+
+/* Create a context on CUDA device `device_id`.  NULL on failure (no device). */
+bsa_ctx *bsa_create(int device_id);
+void bsa_destroy(bsa_ctx *ctx);
+
+/* Message of the last error on this context ("" if none). ctx may be NULL for creation errors. */
+const char *bsa_last_error(const bsa_ctx *ctx);
+
+/*
+ * Parse an NCBI-format substitution matrix exactly as the reference does
+ * (substitution_matrix.rs:96-135): 21x21 row-major table in the file's row order
+ * (A R N D C Q E G H I L K M F P S T W Y V, then X), mirrored writes, X column =
+ * token n-2, X/X forced to -1; aa_index maps a residue byte to its row (every
+ * byte that is not one of the 20 row letters or 'X' maps to 0).  Host only.
+ */
+int bsa_parse_ncbi_matrix(const char *text, size_t len, int32_t score[441], uint8_t aa_index[256]);
+
+/* Scoring used by subsequent alignment calls.  Requires gap_open <= gap_extend <= 0, gap_open < 0. */
+int bsa_set_scoring(bsa_ctx *ctx, const int32_t score[441], const uint8_t aa_index[256],
+                    int32_t gap_open, int32_t gap_extend);
+
+/*
+ * Load (replace) sequence set `set_id` (0..7): n sequences, raw residue bytes packed
+ * back to back, offsets[n+1].  Bytes are uploaded and encoded on the device into the
+ * packed sequence store.  Residues are arbitrary bytes except 255.
+ */
+int bsa_load_sequences(bsa_ctx *ctx, int set_id, const uint8_t *residues_raw,
+                       const uint64_t *offsets, uint32_t n);
+
+/*
+ * The general batched form of align_all_pairs (alignment_protocols.rs:94-110):
+ * for t in [t_begin, t_end) and q in [0, q_counts[t]) align query q (rows) against
+ * template t (columns).  q_counts == NULL means every query for every template
+ * (if_triangle_only = false); q_counts[t] = t is the strict upper triangle of a set
+ * against itself; the host mirror derives other values from the reference's
+ * `template == query -> break` rule.  Result k of pair (q,t) is stored at
+ *   k = sum_{t' in [t_begin,t)} q_counts[t'] + q          (t-major report order)
+ * scores[k]      = GlobalAligner::align's return value (global.rs:143-144)
+ * n_identical[k] = count_identical of the two aligned strings (msa.rs:261-269)
+ * Either output may be NULL.  Returns the number of results through *n_results.
+ */
+int bsa_align_all_pairs(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_counts,
+                        uint32_t t_begin, uint32_t t_end, uint32_t flags, int32_t *scores,
+                        uint32_t *n_identical, uint64_t *n_results);
+
+/* Strict upper triangle of one set: k = t(t-1)/2 + q, q < t.  (cluster_sequences.rs:175-176) */
+int bsa_all_vs_all(bsa_ctx *ctx, int set_id, uint32_t flags, int32_t *scores,
+                   uint32_t *n_identical);
+
+/* Every query against every database sequence: k = t*|Q| + q. (needleman_wunsh.rs:108-109) */
+int bsa_one_vs_many(bsa_ctx *ctx, int q_set, int db_set, uint32_t flags, int32_t *scores,
+                    uint32_t *n_identical);
+
+/*
+ * Cell-balanced contiguous template ranges for n_shards GPUs/ranks:
+ * bounds[0] = 0 <= ... <= bounds[n_shards] = |T|; shard r runs
+ * bsa_align_all_pairs(..., bounds[r], bounds[r+1], ...).  No collective is needed.
+ */
+int bsa_plan_shards(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_counts,
+                    uint32_t n_shards, uint32_t *bounds);
+
+/*
+ * Full alignments for an explicit pair list: score, path glyphs ('*' Match,
+ * '-' Horizontal = gap in query, '|' Vertical = gap in template;
+ * alignment_path.rs:40-47) and n_identical.  path_buf must hold
+ * sum(len_q + len_t) bytes; pair p's path is path_buf[path_off[p] .. path_off[p+1])
+ * after the call (path_off has n_pairs+1 entries, written by the library).
+ * scores / n_identical / path_buf may be NULL.
+ */
+int bsa_align_pairs_paths(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_idx,
+                          const uint32_t *t_idx, uint64_t n_pairs, int32_t *scores,
+                          uint32_t *n_identical, uint8_t *path_buf, uint64_t *path_off);
+
+/* Pinned host memory so device->host result copies run at full PCIe rate. */
+void *bsa_host_alloc_pinned(size_t bytes);
+void bsa_host_free_pinned(void *p);
+
+/* Statistics of the most recent alignment call on this context. */
+typedef struct bsa_stats {
+    uint64_t pairs;          /* pairs aligned */
+    uint64_t cells;          /* sum of len_q*len_t (alignment_protocols.rs:104) */
+    uint64_t padded_cells;   /* cells the kernels actually swept (column padding, pipeline fill) */
+    double kernel_ms;        /* CUDA-event time first launch -> last kernel end */
+    double total_ms;         /* host wall time of the call */
+    uint32_t launches;       /* kernels launched */
+    uint32_t items;          /* work items */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t fallback_pairs; /* pairs routed to the direction-store path */
+    uint32_t reserved;
+} bsa_stats;
+int bsa_get_stats(const bsa_ctx *ctx, bsa_stats *out);
+
+/*
+ * Integer-pipe microbenchmark on the context's GPU: independent chains of the
+ * kernel's own instruction mix (VIADDMNMX / VIMNMX3 / LOP3 / IADD3) on every SM.
+ * Returns lane-operations per second (32 x warp instructions); this is the
+ * measured denominator of the integer/DPX roofline.
+ * which: 0 = the 8-op cell mix, 1 = VIADDMNMX only, 2 = VIMNMX3 only, 3 = LOP3 only,
+ *        4 = IADD3 only, 5 = IMAD only, 6 = VIADDMNMX.S16x2 only
+ */
+int bsa_measure_int_peak(bsa_ctx *ctx, int which, double *lane_ops_per_s, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOSHELL_ALIGN_H */

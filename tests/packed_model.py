@@ -1,0 +1,70 @@
+"""Scalar Python model of the kernels' packed-lane arithmetic (gotoh_kernels.cuh):
+v = score << (cs+2) | prio << cs | count, one signed max per selection.  Used by the
+CPU tests to check the ALGORITHM (tie rules, forward-carried identity, dropped sentinel,
+direction nibbles) against the oracle without a GPU.  Test infrastructure only."""
+
+
+def packed_align(q, t, score, aa, go, ge, cs, want_dirs=False):
+    """q rows (query), t columns (template); raw bytes.  Returns (score, n_identical, dirs)
+    where dirs[(i,j)] is the 4-bit direction code the DIRS kernel stores."""
+    n, m = len(q), len(t)
+    S, U = 1 << (cs + 2), 1 << cs
+    GE, GO, MASK, PH, PV = ge * S, go * S, ~(3 * U), 2 * U, 1 * U
+    gaps = (ord("-"), ord("_"))
+
+    def T(a, b):
+        ident = 1 if (cs > 0 and a == b and a not in gaps) else 0
+        return score[aa[a] * 21 + aa[b]] * S + 3 * U + ident
+
+    Hc = [(go + j * ge) * S for j in range(m)]          # top border H[0][j+1]
+    Fr = [h + GO for h in Hc]                           # eager F for row 1 (opened)
+    dirs = {}
+    hb = go * S
+    for i in range(n):
+        hin, er = hb, hb + GO                           # left border, eager E (opened)
+        hb += GE
+        hd = 0 if i == 0 else (go + (i - 1) * ge) * S   # H[i][0] of the previous row
+        for c in range(m):
+            e = er | PH
+            f = Fr[c] | PV
+            d = hd + T(q[i], t[c])
+            h = max(d, e, f)
+            if want_dirs:
+                dirs[(i + 1, c + 1)] = (h & 3) | (((er | Fr[c]) & 3) << 2)
+            hc = h & MASK
+            hg = hc + GO
+            er = max(e + GE, hg)
+            Fr[c] = max(f + GE, hg)
+            hd, Hc[c] = Hc[c], hc
+    if m == 0:
+        v = 0 if n == 0 else (go + (n - 1) * ge) * S
+    else:
+        v = Hc[m - 1]
+    assert -(1 << 31) <= v < (1 << 31)
+    return v >> (cs + 2), v & (U - 1), dirs
+
+
+def walk_dirs(n, m, dirs):
+    """traceback_kernel's walk over the 4-bit codes (cs = 0 layout)."""
+    out, i, j, st = [], n, m, 0
+    while i > 0 and j > 0:
+        nib = dirs[(i, j)]
+        if st == 0:
+            hd = nib & 3
+            if hd == 3:
+                out.append("*"); i -= 1; j -= 1
+            elif hd == 2:
+                st = 1
+            elif hd == 1:
+                st = 2
+            else:
+                raise RuntimeError("invalid direction")
+        elif st == 1:
+            out.append("-"); j -= 1
+            st = 1 if nib & 8 else 0
+        else:
+            out.append("|"); i -= 1
+            st = 2 if nib & 4 else 0
+    out.extend("-" * j)
+    out.extend("|" * i)
+    return "".join(reversed(out))

@@ -1,0 +1,92 @@
+"""(ii) oracle-vs-oracle: the C restatement against the independent Python one, and the
+kernels' packed-lane arithmetic model against both, on seeded random / homologous pairs
+including dirty bytes, length-1 sequences and several gap settings."""
+import random
+
+import pytest
+
+from bioshell_b200.scoring import ncbi_text
+from oracle import c_oracle, pyoracle
+from packed_model import packed_align, walk_dirs
+
+AA = b"ARNDCQEGHILKMFPSTWYV"
+DIRTY = b"ARNDCQEGHILKMFPSTWYVXBZJUO*-_arndx"
+GAPS = [(-10, -1), (-10, -2), (-11, -1), (-5, -5), (-1, -1), (-12, -3), (-3, 0), (-1, 0)]
+
+
+def rand_seq(rng, n, alphabet):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def mutate(rng, s, alphabet):
+    out = bytearray()
+    for ch in s:
+        u = rng.random()
+        if u < 0.05:
+            continue
+        if u < 0.10:
+            out.extend(rand_seq(rng, rng.randint(1, 3), alphabet))
+        out.append(rng.choice(alphabet) if rng.random() < 0.3 else ch)
+    return bytes(out) or b"A"
+
+
+def pairs(seed, count, maxlen, alphabet):
+    rng = random.Random(seed)
+    for k in range(count):
+        n = rng.randint(1, maxlen)
+        q = rand_seq(rng, n, alphabet)
+        t = mutate(rng, q, alphabet) if k % 2 else rand_seq(rng, rng.randint(1, maxlen), alphabet)
+        yield q, t
+
+
+@pytest.mark.parametrize("matrix", ["BLOSUM62", "PAM30"])
+def test_c_vs_python_restatement(matrix):
+    text = ncbi_text(matrix)
+    sc, ai = c_oracle.parse_ncbi(text)
+    psc, pai = pyoracle.parse_ncbi(text)
+    k = 0
+    for q, t in pairs(11, 400, 40, DIRTY):
+        go, ge = GAPS[k % len(GAPS)]
+        k += 1
+        if ge == 0 and max(len(q), len(t)) < 2:
+            continue
+        lmax = max(len(q), len(t)) + (k % 7) * 50
+        a = c_oracle.align_pair(q, t, sc, ai, go, ge, lmax)
+        b = pyoracle.align_pair(q, t, psc, pai, go, ge, lmax)
+        for key in ("score", "path", "aligned_q", "aligned_t", "n_identical", "len_q", "len_t"):
+            assert a[key] == b[key], (key, q, t, go, ge)
+
+
+@pytest.mark.parametrize("alphabet", [AA, DIRTY])
+def test_packed_lane_model_matches_oracle(alphabet):
+    """The 8-instruction packed cell (score|prio|count in one int, no sentinel, eager E/F)
+    reproduces score, n_identical AND the full traceback of the literal restatement."""
+    text = ncbi_text("BLOSUM62")
+    sc, ai = c_oracle.parse_ncbi(text)
+    psc, pai = pyoracle.parse_ncbi(text)
+    k = 0
+    for q, t in pairs(23, 500, 48, alphabet):
+        go, ge = GAPS[k % len(GAPS)]
+        k += 1
+        if ge == 0 and max(len(q), len(t)) < 2:
+            continue
+        ref = c_oracle.align_pair(q, t, sc, ai, go, ge, max(len(q), len(t)) + 100 * (k % 3))
+        cs = max(len(q), len(t)).bit_length()
+        s, nid, _ = packed_align(q, t, psc, pai, go, ge, cs)
+        assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge)
+        s0, _, dirs = packed_align(q, t, psc, pai, go, ge, 0, want_dirs=True)
+        assert s0 == ref["score"]
+        assert walk_dirs(len(q), len(t), dirs) == ref["path"], (q, t, go, ge)
+
+
+def test_orientation_matters_for_identity_not_score():
+    """SURVEY.md 8a note 5: swapping query and template keeps the score but can change the
+    path/identity, so the kernels must keep the reference's orientation."""
+    sc, ai = c_oracle.parse_ncbi(ncbi_text("BLOSUM62"))
+    differ = 0
+    for q, t in pairs(5, 600, 60, AA):
+        a = c_oracle.align_pair(q, t, sc, ai, -10, -1)
+        b = c_oracle.align_pair(t, q, sc, ai, -10, -1)
+        assert a["score"] == b["score"]
+        differ += a["n_identical"] != b["n_identical"]
+    assert differ > 0
