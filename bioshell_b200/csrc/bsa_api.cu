@@ -27,7 +27,9 @@ constexpr int kMaxSets = 8;
 constexpr int kStreams = 4;
 constexpr int kMaxCodes = 128;
 constexpr size_t kSmemBudget = 200 * 1024;   // profile bytes per CTA we are willing to use
-constexpr int kKMax = 32;
+constexpr int kKMax = 32;          // direction-store kernels
+constexpr int kKStream = 20;       // streaming kernels: beyond 20 columns per lane the row state no
+                                   // longer fits 128 registers (2 CTAs/SM); longer templates take passes
 
 struct DevBuf {
     void* p = nullptr;
@@ -127,14 +129,12 @@ inline int bitlen(uint64_t x) {
 // ---------------- kernel tables ----------------
 typedef void (*KernelFn)(const KArgs);
 KernelFn g_stream_single[kKMax + 1], g_stream_multi[kKMax + 1], g_dirs[kKMax + 1];
-size_t g_vec[kKMax + 1];
 
 template <int K>
 struct Reg {
     static void run() {
         g_stream_single[K] = gotoh_stream_kernel<K, false>;
         g_stream_multi[K] = gotoh_stream_kernel<K, true>;
-        g_vec[K] = KTraits<K>::V;
         Reg<K - 1>::run();
     }
 };
@@ -146,7 +146,7 @@ const int kDirsK[] = {2, 4, 8, 12, 16, 24, 32};
 void register_kernels() {
     static bool done = false;
     if (done) return;
-    Reg<kKMax>::run();
+    Reg<kKStream>::run();
     g_dirs[2] = gotoh_dirs_kernel<2>;
     g_dirs[4] = gotoh_dirs_kernel<4>;
     g_dirs[8] = gotoh_dirs_kernel<8>;
@@ -156,7 +156,7 @@ void register_kernels() {
     g_dirs[32] = gotoh_dirs_kernel<32>;
     done = true;
 }
-size_t smem_for(int K, int C) { return (size_t)(C + 2) * g_vec[K] * 32 * sizeof(uint4); }
+size_t smem_for(int K, int C) { return (size_t)(C + 2) * ((K + 3) / 4) * 32 * sizeof(uint4); }
 
 // largest K whose profile fits the shared-memory budget for an alphabet of C codes
 int k_cap(int C) {
@@ -167,7 +167,7 @@ int k_cap(int C) {
 
 struct KChoice { int K; bool multi; uint32_t npass; };
 KChoice choose_k(uint64_t m, int C) {
-    const int kc = k_cap(C);
+    const int kc = std::min(k_cap(C), kKStream);
     KChoice r;
     if (m <= (uint64_t)32 * kc) {
         r.K = (int)std::max<uint64_t>(1, (m + 31) / 32);
@@ -191,13 +191,22 @@ int choose_dirs_k(uint64_t m, int C) {
     return best;   // multi-pass with the largest K that fits
 }
 
-int launch(bsa_ctx* ctx, KernelFn fn, int K, const KArgs& a, cudaStream_t st) {
-    const size_t smem = smem_for(K, a.C);
+// persistent grid for `n_items` items: one wave of resident CTAs at most
+int grid_for(bsa_ctx* ctx, KernelFn fn, int K, int C, uint32_t n_items, uint32_t* grid) {
+    const size_t smem = smem_for(K, C);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, smem));
     if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "kernel does not fit on an SM");
-    uint32_t grid = (uint32_t)std::min<uint64_t>(a.n_items, (uint64_t)nb * ctx->sms);
+    *grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)nb * ctx->sms);
+    return BSA_OK;
+}
+
+int launch(bsa_ctx* ctx, KernelFn fn, int K, const KArgs& a, cudaStream_t st) {
+    const size_t smem = smem_for(K, a.C);
+    uint32_t grid = 0;
+    int rc = grid_for(ctx, fn, K, a.C, a.n_items, &grid);
+    if (rc) return rc;
     if (grid == 0) return BSA_OK;
     fn<<<grid, kThreads, smem, st>>>(a);
     CK(cudaGetLastError());
@@ -260,7 +269,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             const int K = choose_dirs_k(m, C);
             if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
             const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
-            const uint64_t words = npass * (n + 31) * 32 * W;
+            const uint64_t words = npass * (n + 32) * 32 * W;
             if (!recs.empty() && (dir_words + words) * 4 > dir_budget) break;
             PairRec pr;
             pr.q = r.q; pr.t = r.t; pr.out = r.out;
@@ -325,7 +334,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             memset(&a, 0, sizeof(a));
             a.Q = Q.dev(); a.T = T.dev();
             a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-            a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
             a.items = ctx->items.as<Item>() + gi;
             a.n_items = (uint32_t)(gj - gi);
             a.item_counter = ctx->counters.as<uint32_t>() + group;
@@ -653,11 +662,10 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     if (n_res == 0) return BSA_OK;
 
     const double target_cells = std::min(std::max(total_cells / 60000.0, 1048576.0), 268435456.0);
-    struct Group { std::vector<Item> items; };
+    struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; };
     std::vector<Group> groups(2 * (kKMax + 1));
     std::vector<Fix> fixes;
     std::vector<PairReq> fallback;
-    uint64_t scratch_stride = 0;
     double padded = 0.0;
     const int cs_cap = bitlen(Q.maxlen);
 
@@ -687,7 +695,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         const bool fits = std::max(ub, lb) + 8 < lim;
         const uint64_t m_pad = 32ull * kc.K * kc.npass;
         uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
-        if (kc.multi) xb = std::min<uint64_t>(xb, (uint64_t)kWarpsPerCta * 16384);
+        if (kc.multi) xb = std::min<uint64_t>(xb, 1u << 20);   // bounds the per-CTA boundary slice (8 MiB)
 
         // runs of non-empty queries inside [0, cnt)
         auto e_it = Q.empties.begin();
@@ -715,10 +723,11 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                     Item it;
                     it.t = t; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cs;
                     it.out_base = kbase + q;
-                    groups[kc.K + (kc.multi ? kKMax + 1 : 0)].items.push_back(it);
+                    Group& grp = groups[kc.K + (kc.multi ? kKMax + 1 : 0)];
+                    grp.items.push_back(it);
                     const uint64_t x = Q.off[q2] - Q.off[q];
-                    padded += (double)(x + 31 * kWarpsPerCta) * (double)m_pad;
-                    if (kc.multi) scratch_stride = std::max(scratch_stride, x / kWarpsPerCta + Q.maxlen + 64);
+                    padded += (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
+                    if (kc.multi) grp.stride = std::max(grp.stride, x + 64);   // boundary column of one item
                     q = q2;
                 }
             }
@@ -761,11 +770,18 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         CK(cudaMemcpyAsync(ctx->items.p, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice, s0));
         ctx->stats.h2d_bytes += all.size() * sizeof(Item);
         CK(cudaMemsetAsync(ctx->counters.p, 0, groups.size() * 4, s0));
-        if (scratch_stride) {
-            // every resident warp of a MULTI kernel owns one slice
-            const size_t warps = (size_t)ctx->sms * 8 * kWarpsPerCta;
-            CK(ctx->scratch.ensure(warps * scratch_stride * sizeof(uint2)));
+        // every CTA of every concurrently running MULTI kernel owns its own boundary slice
+        uint64_t scr_total = 0;
+        for (int g : gorder) {
+            if (g <= kKMax) continue;
+            uint32_t grid = 0;
+            rc = grid_for(ctx, g_stream_multi[g - (kKMax + 1)], g - (kKMax + 1), C,
+                          (uint32_t)groups[g].items.size(), &grid);
+            if (rc) return rc;
+            groups[g].scr_off = scr_total;
+            scr_total += (uint64_t)grid * groups[g].stride;
         }
+        if (scr_total) CK(ctx->scratch.ensure(scr_total * sizeof(uint2)));
         CK(cudaEventRecord(ctx->ev_start, s0));
         for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
         int li = 0;
@@ -776,12 +792,13 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             memset(&a, 0, sizeof(a));
             a.Q = Q.dev(); a.T = T.dev();
             a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-            a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
             a.items = ctx->items.as<Item>() + goff[g];
             a.n_items = (uint32_t)groups[g].items.size();
             a.item_counter = ctx->counters.as<uint32_t>() + g;
             a.scores = d_scores; a.nident = d_nid;
-            a.scratch = ctx->scratch.as<uint2>(); a.scratch_stride = (uint32_t)scratch_stride;
+            a.scratch = ctx->scratch.as<uint2>() + groups[g].scr_off;
+            a.scratch_stride = (uint32_t)groups[g].stride;
             rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, ctx->streams[li % kStreams]);
             if (rc) return rc;
             ++li;

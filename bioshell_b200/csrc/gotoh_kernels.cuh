@@ -83,6 +83,7 @@ struct KArgs {
     const uint8_t* isgap;   // C flags: code is '-' or '_' (never identical, msa.rs:264)
     int C;
     int go, ge;
+    int one;                // the constant 1, kept opaque to the compiler (see cell_row)
     const Item* items;
     uint32_t n_items;
     uint32_t* item_counter;
@@ -95,6 +96,13 @@ struct KArgs {
 };
 
 __device__ __forceinline__ int max3_s32(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+// one residue code of the packed store, zero-extended into a full register (kept opaque so the
+// compiler does not start juggling 8/16-bit sub-registers in the hot loop)
+__device__ __forceinline__ uint32_t ld_code(const uint8_t* p) {
+    uint32_t v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ int addmax_s32(int a, int b, int c) { return __viaddmax_s32(a, b, c); }
 
 struct Consts {
@@ -178,120 +186,162 @@ __device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict_
     }
 }
 
+// One systolic step of one lane: a row of K cells.  Hold = H of the previous row in this
+// lane's columns, Hnew = H of this row (the caller ping-pongs the two arrays so no register
+// copies are needed).  `one` is the runtime constant 1: `x * one + y` keeps the two plain
+// additions of the cell on the FMA pipe (IMAD) instead of the ALU pipe, which the six
+// LOP3 / VIMNMX3 / VIADDMNMX instructions saturate.
+template <int K, bool DIRS>
+__device__ __forceinline__ void cell_row(const int (&Hold)[K], int (&Hnew)[K], int (&Fr)[K],
+                                         const int (&T)[K], int hd, int& er, const Consts& cs,
+                                         const int one, uint32_t (&dw)[KTraits<K>::W]) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const int e = er | cs.PH;
+        const int f = Fr[c] | cs.PV;
+        const int d = hd * one + T[c];
+        const int h = max3_s32(d, e, f);
+        if (DIRS) {
+            const uint32_t nib = ((uint32_t)h & 3u) | ((((uint32_t)er | (uint32_t)Fr[c]) & 3u) << 2);
+            dw[c >> 3] = (dw[c >> 3] << 4) | nib;
+        }
+        const int hc = h & cs.MASK;
+        const int hg = hc * one + cs.GO;
+        er = addmax_s32(e, cs.GE, hg);
+        Fr[c] = addmax_s32(f, cs.GE, hg);
+        hd = Hold[c];
+        Hnew[c] = hc;
+    }
+}
+
 // Stream the residues codes[g0 .. g1) (whole sequences, back to back, last residue
 // of each flagged) through the 32 lanes for ONE column block of the template.
-//   FIRST: this block starts at template column 0 (left border is generated),
+//   first: this block starts at template column 0 (left border is generated),
 //          otherwise lane 0 reads the boundary column from `scratch`.
-//   LASTP: this block holds the template's last column (results are emitted),
+//   lastp: this block holds the template's last column (results are emitted),
 //          otherwise lane 31 writes the boundary column to `scratch`.
+// The step loop is unrolled U times (H ping-pongs between two register arrays, so no
+// copies).  A group of U steps in which NO lane meets an end-of-sequence flag runs the
+// fast body (no flag tests, no reconvergence points); otherwise the whole warp takes the
+// checked body.  Extra steps past the end just run into the padding.
 template <int K, bool DIRS, bool MULTI>
 __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
                                              uint64_t g1, const uint4* prof, const uint4* rsH,
                                              const uint4* rsF, const int lane, const bool first,
                                              const bool lastp, const int lane_last,
                                              const int slot_last, const int hdiag0,
-                                             const Consts cs, uint2* __restrict__ scratch,
+                                             const Consts cs, const int one,
+                                             uint2* __restrict__ scratch,
                                              int32_t* __restrict__ scores,
                                              uint32_t* __restrict__ nident, uint64_t out_idx0,
                                              uint32_t* __restrict__ dirs) {
-    constexpr int V = KTraits<K>::V;
     constexpr int W = KTraits<K>::W;
-    constexpr int ROW = KTraits<K>::ROW;
+    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int U = (DIRS || MULTI) ? 2 : (K <= 10 ? 4 : 2);
     const uint32_t X = (uint32_t)(g1 - g0);
     const int span = (MULTI && !lastp) ? 31 : lane_last;
-    const uint32_t nsteps = X + (uint32_t)span;
+    const uint32_t nsteps = (X + (uint32_t)span + (U - 1)) / U * U;
 
-    int Hc[K], Fr[K], T[K];
-    load_vec<K>(Hc, rsH + lane);
+    int Ha[K], Hb[K], Fr[K], T[K];
+    load_vec<K>(Ha, rsH + lane);
     load_vec<K>(Fr, rsF + lane);
     int hdiag = hdiag0;
     int hb = cs.hb0;
     int oh = 0, oe = 0;
     uint32_t emitted = 0;
+    const bool border = !MULTI || first;
+    const bool lane0 = lane == 0;
+    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
 
     const uint8_t* p = codes + g0 - lane;   // lane's position at step 0 (may sit in the padding)
-    uint32_t b = *p;
+    uint32_t b[U], nb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
     uint2 sc_next = make_uint2(0u, 0u);
-    if (MULTI && !first && lane == 0 && X > 0) sc_next = scratch[0];
+    if (MULTI && !first && lane0 && X > 0) sc_next = scratch[0];
 
-    for (uint32_t s = 0; s < nsteps; ++s) {
-        const uint32_t bn = p[1];
-        ++p;
-        const uint4* row = prof + (b & kCodeMask) * ROW + lane;
-        load_vec<K>(T, row);
-
-        int hin = __shfl_up_sync(0xffffffffu, oh, 1);
-        int er = __shfl_up_sync(0xffffffffu, oe, 1);
-        if (lane == 0) {
-            if (!MULTI || first) {
-                // left border: H[i][0] = go + (i-1) ge ; E[i][1] opens from it (global.rs:96-101)
-                hin = hb;
-                er = hb + cs.GO;
-            } else {
-                hin = (int)sc_next.x;
-                er = (int)sc_next.y;
-            }
+    // one step; HO = previous row, HN = this row
+#define BSA_STEP_CORE(HO, HN, B, S)                                                               \
+        load_vec<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB));       \
+        int hin = __shfl_up_sync(0xffffffffu, oh, 1);                                             \
+        int er = __shfl_up_sync(0xffffffffu, oe, 1);                                              \
+        if (lane0) {                                                                              \
+            if (border) { /* H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101) */ \
+                hin = hb;                                                                         \
+                er = hb + cs.GO;                                                                  \
+            } else {                                                                              \
+                hin = (int)sc_next.x;                                                             \
+                er = (int)sc_next.y;                                                              \
+            }                                                                                     \
+        }                                                                                         \
+        if (MULTI && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];                  \
+        hb += cs.GE;                                                                              \
+        const int hd = hdiag;                                                                     \
+        hdiag = hin;                                                                              \
+        uint32_t dw[W];                                                                           \
+        _Pragma("unroll") for (int w = 0; w < W; ++w) dw[w] = 0u;                                 \
+        cell_row<K, DIRS>(HO, HN, Fr, T, hd, er, cs, one, dw);                                    \
+        oh = HN[K - 1];                                                                           \
+        oe = er;                                                                                  \
+        if (DIRS) {                                                                               \
+            uint32_t* dp = dirs + ((size_t)(S)*32 + lane) * W;                                    \
+            _Pragma("unroll") for (int w = 0; w < W; ++w) dp[w] = dw[w];                          \
+        }                                                                                         \
+        if (MULTI && !lastp && lane == 31) {                                                      \
+            const uint32_t pos = (S)-31u; /* wraps for S < 31 -> fails the bound test */          \
+            if (pos < X) scratch[pos] = make_uint2((uint32_t)oh, (uint32_t)oe);                   \
         }
-        if (MULTI && !first && lane == 0 && s + 1 < X) sc_next = scratch[s + 1];
-        hb += cs.GE;
-
-        int hd = hdiag;
-        hdiag = hin;
-        uint32_t dw[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) dw[w] = 0u;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-            const int e = er | cs.PH;
-            const int f = Fr[c] | cs.PV;
-            const int d = hd + T[c];
-            const int h = max3_s32(d, e, f);
-            if (DIRS) {
-                const uint32_t nib = ((uint32_t)h & 3u) | ((((uint32_t)er | (uint32_t)Fr[c]) & 3u) << 2);
-                dw[c >> 3] = (dw[c >> 3] << 4) | nib;
-            }
-            const int hc = h & cs.MASK;
-            const int hg = hc + cs.GO;
-            er = addmax_s32(e, cs.GE, hg);
-            Fr[c] = addmax_s32(f, cs.GE, hg);
-            hd = Hc[c];
-            Hc[c] = hc;
-        }
-        oh = Hc[K - 1];
-        oe = er;
-
-        if (DIRS) {
-            uint32_t* dp = dirs + ((size_t)s * 32 + lane) * W;
-#pragma unroll
-            for (int w = 0; w < W; ++w) dp[w] = dw[w];
-        }
-        if (MULTI && !lastp && lane == 31) {
-            const uint32_t pos = s - 31u;     // wraps for s < 31 -> fails the bound test
-            if (pos < X) scratch[pos] = make_uint2((uint32_t)oh, (uint32_t)oe);
-        }
-
-        if (b & kLastFlag) {
-            // end of a query: emit H[n][m] from the lane that owns column m, then put the
-            // lane back on the top border for the next query of the stream.
-            const uint32_t pos = s - (uint32_t)lane;
-            const bool valid = pos < X;
-            if (lastp && valid && lane == lane_last) {
-                int v = 0;
-#pragma unroll
-                for (int c = 0; c < K; ++c)
-                    if (c == slot_last) v = Hc[c];
-                const uint64_t k = out_idx0 + emitted;
-                if (scores) scores[k] = v >> (cs.cs + 2);
-                if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);
-            }
-            emitted += valid ? 1u : 0u;
-            load_vec<K>(Hc, rsH + lane);
-            load_vec<K>(Fr, rsF + lane);
-            hdiag = hdiag0;
-            hb = cs.hb0;
-        }
-        b = bn;
+#define BSA_STEP_FAST(HO, HN, B, S) { BSA_STEP_CORE(HO, HN, B, S) }
+#define BSA_STEP(HO, HN, B, S)                                                                    \
+    {                                                                                             \
+        BSA_STEP_CORE(HO, HN, B, S)                                                               \
+        if ((B)&kLastFlag) {                                                                      \
+            /* end of a query: emit H[n][m] from the lane that owns column m, then put the */     \
+            /* lane back on the top border for the next query of the stream.               */     \
+            const uint32_t pos = (S) - (uint32_t)lane;                                            \
+            const bool valid = pos < X;                                                           \
+            if (lastp && valid && lane == lane_last) {                                            \
+                int v = 0;                                                                        \
+                _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = HN[c];      \
+                const uint64_t k = out_idx0 + emitted;                                            \
+                if (scores) scores[k] = v >> (cs.cs + 2);                                         \
+                if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                       \
+            }                                                                                     \
+            emitted += valid ? 1u : 0u;                                                           \
+            load_vec<K>(HN, rsH + lane);                                                          \
+            load_vec<K>(Fr, rsF + lane);                                                          \
+            hdiag = hdiag0;                                                                       \
+            hb = cs.hb0;                                                                          \
+        }                                                                                         \
     }
+
+    for (uint32_t s = 0; s < nsteps; s += U) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            nb[u] = ld_code(p + U + u);   // prefetch the next group's residues
+            any |= b[u];
+        }
+        p += U;
+        if (!__any_sync(0xffffffffu, any & kLastFlag)) {
+#pragma unroll
+            for (int u = 0; u < U; u += 2) {
+                BSA_STEP_FAST(Ha, Hb, b[u], s + u)
+                BSA_STEP_FAST(Hb, Ha, b[u + 1], s + u + 1)
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u += 2) {
+                BSA_STEP(Ha, Hb, b[u], s + u)
+                BSA_STEP(Hb, Ha, b[u + 1], s + u + 1)
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) b[u] = nb[u];
+    }
+#undef BSA_STEP
+#undef BSA_STEP_FAST
+#undef BSA_STEP_CORE
 }
 
 __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
@@ -319,18 +369,27 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift) {
     return cs;
 }
 
-// Score + identity for (template, query range) items.  Persistent CTAs pull items from
-// an atomic counter; the CTA's warps split the item's residue stream evenly.
+// Score + identity for (template, query range) items.  Persistent CTAs pull items from an
+// atomic counter and build the template's profile once; the item's residue stream is cut
+// into chunks of whole queries that the CTA's warps pull from a shared counter (warps do
+// not progress at the same rate -- the issue arbiter is not fair -- so a static split
+// would leave the fast warps waiting at the item's closing barrier).
+template <int K>
+struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= 8 ? 3 : 2); };
+
+constexpr uint32_t kChunkResidues = 3072;   // stream residues per chunk (fill/drain is 31 steps)
+constexpr uint32_t kMaxChunks = 256;
+
 template <int K, bool MULTI>
-__global__ void __launch_bounds__(kThreads) gotoh_stream_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_kernel(const KArgs a) {
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_item;
+    __shared__ uint32_t s_chunk;
     constexpr int ROW = KTraits<K>::ROW;
     uint4* prof = smem;
     uint4* rsH = smem + (size_t)a.C * ROW;
     uint4* rsF = rsH + ROW;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -343,24 +402,18 @@ __global__ void __launch_bounds__(kThreads) gotoh_stream_kernel(const KArgs a) {
         const uint8_t* tc = a.T.codes + t0;
         const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift);
 
-        // this warp's share of the item's residue stream (whole queries)
         const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
         const uint64_t span = x1 - x0;
-        const uint32_t qa = warp == 0 ? it.q_begin
-                                      : lower_bound_off(a.Q.off, it.q_begin, it.q_end,
-                                                        x0 + span * warp / kWarpsPerCta);
-        const uint32_t qb = warp == kWarpsPerCta - 1
-                                ? it.q_end
-                                : lower_bound_off(a.Q.off, it.q_begin, it.q_end,
-                                                  x0 + span * (warp + 1) / kWarpsPerCta);
-        const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+        uint32_t nch = (uint32_t)((span + kChunkResidues - 1) / kChunkResidues);
+        nch = nch < (uint32_t)kWarpsPerCta ? (uint32_t)kWarpsPerCta : (nch > kMaxChunks ? kMaxChunks : nch);
         const uint32_t npass = MULTI ? (m + 32 * K - 1) / (32 * K) : 1u;
-        uint2* scratch = MULTI ? a.scratch + (size_t)(blockIdx.x * kWarpsPerCta + warp) * a.scratch_stride
-                               : nullptr;
+        // MULTI: the boundary column of the whole item, addressed by stream position
+        uint2* scratch = MULTI ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : nullptr;
 
         for (uint32_t pass = 0; pass < npass; ++pass) {
             const uint32_t colbase = pass * 32 * K;
-            __syncthreads();   // previous profile is no longer read by anyone
+            __syncthreads();   // previous profile / chunk counter are no longer in use
+            if (threadIdx.x == 0) s_chunk = 0;
             build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
             __syncthreads();
             const bool lastp = (pass + 1 == npass);
@@ -368,12 +421,24 @@ __global__ void __launch_bounds__(kThreads) gotoh_stream_kernel(const KArgs a) {
             const int slot_last = (int)((m - 1 - colbase) % K);
             const long long jl = (long long)colbase + (long long)lane * K;  // DP column left of the lane
             const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * (1 << (cs.cs + 2)));
-            if (g1 > g0)
-                stream_block<K, false, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
-                                              lastp, lastp ? lane_last : 31, slot_last, hdiag0, cs,
-                                              scratch, a.scores, a.nident,
-                                              it.out_base + (qa - it.q_begin), nullptr);
-            if (MULTI) __syncwarp();
+            for (;;) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&s_chunk, 1u);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= nch) break;
+                // chunk c = the queries whose first residue falls in its share of the stream
+                const uint32_t qa = c == 0 ? it.q_begin
+                                           : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + span * c / nch);
+                const uint32_t qb = c + 1 == nch ? it.q_end
+                                                 : lower_bound_off(a.Q.off, it.q_begin, it.q_end,
+                                                                   x0 + span * (c + 1) / nch);
+                const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+                if (g1 > g0)
+                    stream_block<K, false, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
+                                                  lastp, lastp ? lane_last : 31, slot_last, hdiag0, cs,
+                                                  a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
+                                                  a.nident, it.out_base + (qa - it.q_begin), nullptr);
+            }
         }
     }
 }
@@ -419,13 +484,13 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
                 const PairRec pr = a.pairs[pi];
                 const uint64_t g0 = a.Q.off[pr.q], g1 = a.Q.off[pr.q + 1];
                 const uint32_t n = (uint32_t)(g1 - g0);
-                // plane of this pass: (n + 31) steps x 32 lanes x W words
-                uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 31) * 32 * W;
+                // plane of this pass: (n + 32) steps x 32 lanes x W words
+                uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 32) * 32 * W;
                 // the boundary column must survive until this pair's next pass (passes are
                 // the outer loop because the CTA shares the profile), so it is per pair
                 stream_block<K, true, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
                                             lastp, lastp ? lane_last : 31, slot_last, hdiag0, cs,
-                                            a.scratch + pr.scr_off, a.scores, nullptr, pr.out, dirs);
+                                            a.one, a.scratch + pr.scr_off, a.scores, nullptr, pr.out, dirs);
                 __syncwarp();
             }
         }
@@ -459,7 +524,7 @@ __global__ void traceback_kernel(const TraceArgs a) {
     const uint32_t n = (uint32_t)(a.Q.off[pr.q + 1] - a.Q.off[pr.q]);
     const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - a.T.off[pr.t]);
     const uint32_t K = pr.k, W = (K + 7) / 8, BK = 32 * K;
-    const size_t plane = (size_t)(n + 31) * 32 * W;
+    const size_t plane = (size_t)(n + 32) * 32 * W;
     const uint32_t* dirs = a.dirs + pr.dir_off;
     uint8_t* out = a.path ? a.path + pr.path_off : nullptr;
     uint32_t pos = n + m, i = n, j = m, nid = 0;

@@ -15,7 +15,7 @@ constexpr int kPeakChains = 8;
 constexpr int kPeakIters = 4096;
 
 template <int WHICH>
-__global__ void __launch_bounds__(256) int_peak_kernel(int seed, int* sink, unsigned long long* clk) {
+__global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int* sink, unsigned long long* clk) {
     int a[kPeakChains], b[kPeakChains], c[kPeakChains];
 #pragma unroll
     for (int i = 0; i < kPeakChains; ++i) {
@@ -34,13 +34,13 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int* sink, unsi
 #pragma unroll
         for (int i = 0; i < kPeakChains; ++i) {
             if (WHICH == 0) {
-                // the alignment cell: 3 LOP3 + 2 IADD3 + VIMNMX3 + 2 VIADDMNMX
+                // the alignment cell: 3 LOP3 + VIMNMX3 + 2 VIADDMNMX (ALU pipe) + 2 IMAD (FMA pipe)
                 const int e = a[i] | ph;
                 const int f = b[i] | pv;
-                const int d = c[i] + ge;
+                const int d = c[i] * one + ge;
                 const int h = __vimax3_s32(d, e, f);
                 const int hc = h & mask;
-                const int hg = hc + go;
+                const int hg = hc * one + go;
                 a[i] = __viaddmax_s32(e, ge, hg);
                 b[i] = __viaddmax_s32(f, ge, hg);
                 c[i] = hc;
@@ -94,13 +94,13 @@ inline cudaError_t measure_int_peak(int which, int sms, cudaStream_t st, double*
     const int blocks = sms * 8;
     auto go = [&](void) {
         switch (which) {
-            case 0: int_peak_kernel<0><<<blocks, 256, 0, st>>>(1, sink, clk); break;
-            case 1: int_peak_kernel<1><<<blocks, 256, 0, st>>>(1, sink, clk); break;
-            case 2: int_peak_kernel<2><<<blocks, 256, 0, st>>>(1, sink, clk); break;
-            case 3: int_peak_kernel<3><<<blocks, 256, 0, st>>>(1, sink, clk); break;
-            case 4: int_peak_kernel<4><<<blocks, 256, 0, st>>>(1, sink, clk); break;
-            case 5: int_peak_kernel<5><<<blocks, 256, 0, st>>>(1, sink, clk); break;
-            default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, sink, clk); break;
+            case 0: int_peak_kernel<0><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            case 1: int_peak_kernel<1><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            case 2: int_peak_kernel<2><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            case 3: int_peak_kernel<3><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            case 4: int_peak_kernel<4><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            case 5: int_peak_kernel<5><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
         }
     };
     for (int w = 0; w < 3; ++w) go();
