@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -662,7 +663,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     if (n_res == 0) return BSA_OK;
 
     const double target_cells = std::min(std::max(total_cells / 60000.0, 1048576.0), 268435456.0);
-    struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; };
+    struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0, swept = 0; };
     std::vector<Group> groups(2 * (kKMax + 1));
     std::vector<Fix> fixes;
     std::vector<PairReq> fallback;
@@ -695,7 +696,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         const bool fits = std::max(ub, lb) + 8 < lim;
         const uint64_t m_pad = 32ull * kc.K * kc.npass;
         uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
-        if (kc.multi) xb = std::min<uint64_t>(xb, 1u << 20);   // bounds the per-CTA boundary slice (8 MiB)
+        // short templates: keep items small enough that their group still fills the GPU;
+        // multi-pass: this also bounds the per-CTA boundary slice (1 MiB)
+        xb = std::min<uint64_t>(xb, 1u << 17);
 
         // runs of non-empty queries inside [0, cnt)
         auto e_it = Q.empties.begin();
@@ -726,7 +729,10 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                     Group& grp = groups[kc.K + (kc.multi ? kKMax + 1 : 0)];
                     grp.items.push_back(it);
                     const uint64_t x = Q.off[q2] - Q.off[q];
-                    padded += (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
+                    const double sw = (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
+                    padded += sw;
+                    grp.swept += sw;
+                    grp.cells += (double)x * (double)m;
                     if (kc.multi) grp.stride = std::max(grp.stride, x + 64);   // boundary column of one item
                     q = q2;
                 }
@@ -784,6 +790,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         if (scr_total) CK(ctx->scratch.ensure(scr_total * sizeof(uint2)));
         CK(cudaEventRecord(ctx->ev_start, s0));
         for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+        // BSA_PROFILE_GROUPS=1: run the groups one after another and report each one's rate
+        const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
+        std::vector<cudaEvent_t> pev;
         int li = 0;
         for (int g : gorder) {
             const bool multi = g > kKMax;
@@ -799,9 +808,32 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             a.scores = d_scores; a.nident = d_nid;
             a.scratch = ctx->scratch.as<uint2>() + groups[g].scr_off;
             a.scratch_stride = (uint32_t)groups[g].stride;
-            rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, ctx->streams[li % kStreams]);
+            if (prof_groups) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, s0);
+                rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, s0);
+                cudaEventRecord(e1, s0);
+                pev.push_back(e0); pev.push_back(e1);
+            } else {
+                rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, ctx->streams[li % kStreams]);
+            }
             if (rc) return rc;
             ++li;
+        }
+        if (prof_groups) {
+            cudaStreamSynchronize(s0);
+            size_t gi = 0;
+            for (int g : gorder) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, pev[2 * gi], pev[2 * gi + 1]);
+                fprintf(stderr, "[bsa group] K=%2d multi=%d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n",
+                        g > kKMax ? g - (kKMax + 1) : g, g > kKMax ? 1 : 0, groups[g].items.size(), groups[g].cells,
+                        groups[g].cells > 0 ? groups[g].swept / groups[g].cells : 0.0, ms,
+                        ms > 0 ? groups[g].cells / 1e6 / ms : 0.0);
+                cudaEventDestroy(pev[2 * gi]); cudaEventDestroy(pev[2 * gi + 1]);
+                ++gi;
+            }
         }
         for (int i = 1; i < kStreams; ++i) {
             CK(cudaEventRecord(ctx->ev_s[i], ctx->streams[i]));

@@ -375,7 +375,7 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift) {
 // not progress at the same rate -- the issue arbiter is not fair -- so a static split
 // would leave the fast warps waiting at the item's closing barrier).
 template <int K>
-struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= 8 ? 3 : 2); };
+struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= 12 ? 3 : 2); };
 
 constexpr uint32_t kChunkResidues = 3072;   // stream residues per chunk (fill/drain is 31 steps)
 constexpr uint32_t kMaxChunks = 256;

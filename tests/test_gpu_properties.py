@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import bioshell_b200 as bs
-from bioshell_b200 import synth
+from bioshell_b200 import sharding, synth
 from oracle import c_oracle
 
 pytestmark = pytest.mark.gpu
@@ -88,8 +88,10 @@ def test_sharded_ranges_concatenate_to_the_whole(ctx):
     ctx.load_sequences(0, res, off)
     counts = np.arange(n, dtype=np.uint32)
     whole = ctx.align_all_pairs(0, 0, counts)
+    lens = np.diff(off.astype(np.int64))
     for shards in (2, 4, 8):
         b = ctx.plan_shards(0, 0, counts, shards)
+        assert np.array_equal(b.astype(np.int64), sharding.plan_shards(lens, lens, counts, shards))
         assert b[0] == 0 and b[-1] == n and np.all(np.diff(b.astype(np.int64)) >= 0)
         parts = [ctx.align_all_pairs(0, 0, counts, int(b[i]), int(b[i + 1])) for i in range(shards)]
         assert np.array_equal(np.concatenate([p[0] for p in parts]), whole[0])
