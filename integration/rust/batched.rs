@@ -1,0 +1,133 @@
+// bioshell-seq/src/alignment/batched.rs -- SOURCE ONLY (no rustc in the build image).
+//
+// The new batched entry points next to `align_all_pairs`
+// (bioshell-seq/src/alignment/alignment_protocols.rs:83-115), behind the existing module:
+// add `mod batched; pub use batched::*;` to bioshell-seq/src/alignment/mod.rs:15-20.
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int};
+
+use crate::alignment::{aligned_sequences, AlignmentPath, AlignmentReporter};
+use crate::scoring::{SubstitutionMatrix, SubstitutionMatrixList};
+use crate::sequence::Sequence;
+
+#[repr(C)]
+pub struct BsaCtx { _private: [u8; 0] }
+
+extern "C" {
+    fn bsa_create(device_id: c_int) -> *mut BsaCtx;
+    fn bsa_destroy(ctx: *mut BsaCtx);
+    fn bsa_last_error(ctx: *const BsaCtx) -> *const c_char;
+    fn bsa_set_scoring(ctx: *mut BsaCtx, score: *const i32, aa_index: *const u8, gap_open: i32, gap_extend: i32) -> c_int;
+    fn bsa_load_sequences(ctx: *mut BsaCtx, set_id: c_int, residues: *const u8, offsets: *const u64, n: u32) -> c_int;
+    fn bsa_align_all_pairs(ctx: *mut BsaCtx, q_set: c_int, t_set: c_int, q_counts: *const u32, t_begin: u32,
+                           t_end: u32, flags: u32, scores: *mut i32, n_identical: *mut u32, n_results: *mut u64) -> c_int;
+    fn bsa_align_pairs_paths(ctx: *mut BsaCtx, q_set: c_int, t_set: c_int, q_idx: *const u32, t_idx: *const u32,
+                             n_pairs: u64, scores: *mut i32, n_identical: *mut u32, path_buf: *mut u8,
+                             path_off: *mut u64) -> c_int;
+}
+
+const BSA_WANT_SCORE: u32 = 1;
+const BSA_WANT_IDENTICAL: u32 = 2;
+
+/// Scores and identical-residue counts in the report order of `align_all_pairs`
+/// (template-major: for t { for q { .. } }, alignment_protocols.rs:94-102).
+pub struct PairResults {
+    pub scores: Vec<i32>,
+    pub n_identical: Vec<u32>,
+    /// number of queries aligned against template t (the position of the triangle `break`)
+    pub q_counts: Vec<u32>,
+}
+
+pub struct GpuAligner { ctx: *mut BsaCtx }
+
+impl GpuAligner {
+    pub fn new(device: i32) -> Result<Self, String> {
+        let ctx = unsafe { bsa_create(device) };
+        if ctx.is_null() {
+            return Err(unsafe { CStr::from_ptr(bsa_last_error(std::ptr::null())) }.to_string_lossy().into());
+        }
+        Ok(GpuAligner { ctx })
+    }
+
+    fn check(&self, rc: c_int) -> Result<(), String> {
+        if rc == 0 { Ok(()) } else {
+            Err(unsafe { CStr::from_ptr(bsa_last_error(self.ctx)) }.to_string_lossy().into())
+        }
+    }
+
+    fn load(&self, set_id: i32, seqs: &[Sequence]) -> Result<(), String> {
+        let mut residues: Vec<u8> = Vec::new();
+        let mut offsets: Vec<u64> = vec![0];
+        for s in seqs {
+            residues.extend_from_slice(s.as_u8());
+            offsets.push(residues.len() as u64);
+        }
+        self.check(unsafe { bsa_load_sequences(self.ctx, set_id, residues.as_ptr(), offsets.as_ptr(), seqs.len() as u32) })
+    }
+
+    /// The inner-loop trip count of alignment_protocols.rs:96-97 for every template.
+    fn triangle_counts(queries: &[Sequence], templates: &[Sequence], triangle: bool) -> Vec<u32> {
+        templates.iter().map(|t| {
+            if !triangle { return queries.len() as u32; }
+            queries.iter().position(|q| q == t).unwrap_or(queries.len()) as u32
+        }).collect()
+    }
+
+    /// Batched replacement of the `align_all_pairs` double loop: no strings are built.
+    pub fn align_pairs_batched(&self, queries: &[Sequence], templates: &[Sequence], matrix: SubstitutionMatrixList,
+                               gap_open: i32, gap_extend: i32, if_triangle_only: bool) -> Result<PairResults, String> {
+        let m = SubstitutionMatrix::load(matrix);
+        let mut aa = [0u8; 256];
+        aa[..255].copy_from_slice(&m.aa_indexes);          // pub(crate) fields, substitution_matrix.rs:31-32
+        self.check(unsafe { bsa_set_scoring(self.ctx, m.score.as_ptr(), aa.as_ptr(), gap_open, gap_extend) })?;
+        self.load(0, queries)?;
+        self.load(1, templates)?;
+        let q_counts = Self::triangle_counts(queries, templates, if_triangle_only);
+        let n: u64 = q_counts.iter().map(|&c| c as u64).sum();
+        let mut scores = vec![0i32; n as usize];
+        let mut nid = vec![0u32; n as usize];
+        let mut n_res = 0u64;
+        self.check(unsafe {
+            bsa_align_all_pairs(self.ctx, 0, 1, q_counts.as_ptr(), 0, templates.len() as u32,
+                                BSA_WANT_SCORE | BSA_WANT_IDENTICAL, scores.as_mut_ptr(), nid.as_mut_ptr(), &mut n_res)
+        })?;
+        Ok(PairResults { scores, n_identical: nid, q_counts })
+    }
+
+    /// Drop-in for `align_all_pairs` with a reporter: same pairs, same (t-major) order, the
+    /// aligned `Sequence`s built from the GPU traceback paths.
+    pub fn align_all_pairs<R: AlignmentReporter>(&self, queries: &Vec<Sequence>, templates: &Vec<Sequence>,
+            matrix: SubstitutionMatrixList, gap_open: i32, gap_extend: i32, if_triangle_only: bool,
+            reporter: &mut R) -> Result<(), String> {
+        let m = SubstitutionMatrix::load(matrix);
+        let mut aa = [0u8; 256];
+        aa[..255].copy_from_slice(&m.aa_indexes);
+        self.check(unsafe { bsa_set_scoring(self.ctx, m.score.as_ptr(), aa.as_ptr(), gap_open, gap_extend) })?;
+        self.load(0, queries)?;
+        self.load(1, templates)?;
+        let counts = Self::triangle_counts(queries, templates, if_triangle_only);
+        for (t, &cnt) in counts.iter().enumerate() {
+            if cnt == 0 { continue; }
+            let q_idx: Vec<u32> = (0..cnt).collect();
+            let t_idx: Vec<u32> = vec![t as u32; cnt as usize];
+            let cap: usize = q_idx.iter().map(|&q| queries[q as usize].len() + templates[t].len()).sum();
+            let mut path_buf = vec![0u8; cap];
+            let mut path_off = vec![0u64; cnt as usize + 1];
+            self.check(unsafe {
+                bsa_align_pairs_paths(self.ctx, 0, 1, q_idx.as_ptr(), t_idx.as_ptr(), cnt as u64, std::ptr::null_mut(),
+                                      std::ptr::null_mut(), path_buf.as_mut_ptr(), path_off.as_mut_ptr())
+            })?;
+            for q in 0..cnt as usize {
+                let glyphs = std::str::from_utf8(&path_buf[path_off[q] as usize..path_off[q + 1] as usize]).unwrap();
+                let path = AlignmentPath::try_from(glyphs).unwrap();      // alignment_path.rs:88-105
+                let (ali_q, ali_t) = aligned_sequences(&path, &queries[q], &templates[t], '-');
+                reporter.report(&ali_q, &ali_t);                          // alignment_protocols.rs:102
+            }
+        }
+        Ok(())
+    }
+}
+
+impl Drop for GpuAligner {
+    fn drop(&mut self) { unsafe { bsa_destroy(self.ctx) } }
+}
