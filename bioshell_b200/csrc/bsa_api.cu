@@ -98,7 +98,7 @@ struct bsa_ctx {
     SeqSet sets[kMaxSets];
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
-        raw, lut, presence;
+        raw, lut, presence, progress, wave_items;
     bsa_stats stats;
 };
 
@@ -263,11 +263,15 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         // ---- take a batch that fits the direction budget ----
         std::vector<PairRec> recs;
         std::vector<uint32_t> rec_req;
-        uint64_t dir_words = 0, scr_entries = 0, path_bytes = 0;
+        std::vector<uint2> wave_items;      // (rec index, column block) in dependency order
+        uint64_t dir_words = 0, scr_entries = 0, path_bytes = 0, n_prog = 0;
+        // K3: templates this long run their column blocks as a wavefront over many warps
+        const int wave_warps = (int)std::min<size_t>(kWaveWarps, kSmemBudget / ((size_t)(C + 2) * 64 * sizeof(uint4)));
         while (pos < order.size()) {
             const PairReq& r = reqs[order[pos]];
             const uint64_t n = Q.len(r.q), m = T.len(r.t);
-            const int K = choose_dirs_k(m, C);
+            const bool wave = m >= 4096 && wave_warps >= 1;   // >= 16 column blocks of 256
+            const int K = wave ? kWaveK : choose_dirs_k(m, C);
             if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
             const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
             const uint64_t words = npass * (n + 32) * 32 * W;
@@ -277,9 +281,16 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             pr.dir_off = dir_words;
             pr.scr_off = scr_entries;
             pr.path_off = path_bytes;
-            pr.k = (uint32_t)K; pr.pad = 0;
+            pr.k = (uint32_t)K;
+            pr.prog_off = wave ? (uint32_t)n_prog : 0xffffffffu;
             dir_words += words;
-            scr_entries += npass > 1 ? n : 0;
+            if (wave) {
+                scr_entries += (npass - 1) * n;
+                for (uint64_t ps = 0; ps < npass; ++ps) wave_items.push_back(make_uint2((uint32_t)recs.size(), (uint32_t)ps));
+                n_prog += npass;
+            } else {
+                scr_entries += npass > 1 ? n : 0;
+            }
             path_bytes += n + m;
             recs.push_back(pr);
             rec_req.push_back(order[pos]);
@@ -291,6 +302,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         for (size_t i = 0; i < recs.size();) {
             size_t j = i;
             while (j < recs.size() && recs[j].t == recs[i].t) ++j;
+            if (recs[i].prog_off != 0xffffffffu) { i = j; continue; }   // wavefront pairs: see below
             // keep CTAs busy: at most 4 pairs per warp per item
             for (size_t b = i; b < j; b += 4 * kWarpsPerCta) {
                 Item it;
@@ -347,6 +359,35 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             if (rc) return rc;
             gi = gj;
             ++group;
+        }
+        if (!wave_items.empty()) {
+            CK(ctx->wave_items.ensure(wave_items.size() * sizeof(uint2)));
+            CK(ctx->progress.ensure(n_prog * 4));
+            CK(cudaMemcpyAsync(ctx->wave_items.p, wave_items.data(), wave_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(ctx->progress.p, 0, n_prog * 4, st));
+            KArgs a;
+            memset(&a, 0, sizeof(a));
+            a.Q = Q.dev(); a.T = T.dev();
+            a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
+            a.n_items = (uint32_t)wave_items.size();
+            a.item_counter = ctx->counters.as<uint32_t>() + 63;
+            a.scores = d_scores;
+            a.scratch = ctx->scratch.as<uint2>();
+            a.pairs = ctx->pairs.as<PairRec>();
+            a.dirs = ctx->dirs.as<uint32_t>();
+            a.progress = ctx->progress.as<uint32_t>();
+            a.wave_items = ctx->wave_items.as<uint2>();
+            const size_t smem = (size_t)wave_warps * (C + 2) * 64 * sizeof(uint4);
+            CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, smem));
+            if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "wavefront kernel does not fit on an SM");
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((wave_items.size() + wave_warps - 1) / wave_warps,
+                                                               (uint64_t)nb * ctx->sms);
+            gotoh_wave_kernel<<<grid, wave_warps * 32, smem, st>>>(a);
+            CK(cudaGetLastError());
+            ctx->stats.launches++;
         }
         TraceArgs ta;
         ta.Q = Q.dev(); ta.T = T.dev();
@@ -436,7 +477,7 @@ void bsa_destroy(bsa_ctx* c) {
     for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
-                      &c->presence, &c->d_subst, &c->d_isgap};
+                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -662,7 +703,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     ctx->stats.cells = (uint64_t)total_cells;
     if (n_res == 0) return BSA_OK;
 
-    const double target_cells = std::min(std::max(total_cells / 60000.0, 1048576.0), 268435456.0);
+    const double target_cells = std::min(std::max(total_cells / 40000.0, 1048576.0), 268435456.0);
     struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0, swept = 0; };
     std::vector<Group> groups(2 * (kKMax + 1));
     std::vector<Fix> fixes;
@@ -697,8 +738,8 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         const uint64_t m_pad = 32ull * kc.K * kc.npass;
         uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
         // short templates: keep items small enough that their group still fills the GPU;
-        // multi-pass: this also bounds the per-CTA boundary slice (1 MiB)
-        xb = std::min<uint64_t>(xb, 1u << 17);
+        // multi-pass: this also bounds the per-CTA boundary slice (2 MiB)
+        xb = std::min<uint64_t>(xb, 1u << 18);
 
         // runs of non-empty queries inside [0, cnt)
         auto e_it = Q.empties.begin();

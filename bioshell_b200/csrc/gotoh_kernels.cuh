@@ -68,7 +68,7 @@ struct PairRec {
     uint64_t scr_off;   // entry offset of this pair's boundary column (multi-pass templates)
     uint64_t path_off;  // byte offset of this pair's path slot (len_q + len_t bytes)
     uint32_t k;         // columns per lane the fill kernel used
-    uint32_t pad;
+    uint32_t prog_off;  // wavefront mode: first progress counter of this pair (one per column block)
 };
 
 struct SeqStoreDev {
@@ -93,6 +93,8 @@ struct KArgs {
     uint32_t scratch_stride;  // entries per warp
     const PairRec* pairs;   // DIRS
     uint32_t* dirs;         // DIRS
+    uint32_t* progress;     // WAVE: boundary hand-off counters
+    const uint2* wave_items;  // WAVE: (pair index, column block), in dependency order
 };
 
 __device__ __forceinline__ int max3_s32(int a, int b, int c) { return __vimax3_s32(a, b, c); }
@@ -224,19 +226,36 @@ __device__ __forceinline__ void cell_row(const int (&Hold)[K], int (&Hnew)[K], i
 // copies).  A group of U steps in which NO lane meets an end-of-sequence flag runs the
 // fast body (no flag tests, no reconvergence points); otherwise the whole warp takes the
 // checked body.  Extra steps past the end just run into the padding.
-template <int K, bool DIRS, bool MULTI>
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// WAVE: the column blocks of one long pair run CONCURRENTLY in different warps (K3, the
+// intra-task wavefront).  The block to the left publishes how many boundary entries it has
+// written (`prog_out`, release store every 32 rows); this block waits on `prog_in` (acquire)
+// before it consumes them.  Without WAVE, scratch_out == scratch and the pointers are null.
+template <int K, bool DIRS, bool MULTI, bool WAVE = false>
 __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
                                              uint64_t g1, const uint4* prof, const uint4* rsH,
                                              const uint4* rsF, const int lane, const bool first,
                                              const bool lastp, const int lane_last,
                                              const int slot_last, const int hdiag0,
                                              const Consts cs, const int one,
-                                             uint2* __restrict__ scratch,
+                                             uint2* scratch,
                                              int32_t* __restrict__ scores,
                                              uint32_t* __restrict__ nident, uint64_t out_idx0,
-                                             uint32_t* __restrict__ dirs) {
+                                             uint32_t* __restrict__ dirs, uint2* scratch_out = nullptr,
+                                             const uint32_t* prog_in = nullptr,
+                                             uint32_t* prog_out = nullptr) {
     constexpr int W = KTraits<K>::W;
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    if (!WAVE) scratch_out = scratch;
+    uint32_t avail = 0;   // WAVE: boundary entries known to be published by the left block
     constexpr int U = (DIRS || MULTI) ? 2 : (K <= 10 ? 4 : 2);
     const uint32_t X = (uint32_t)(g1 - g0);
     const int span = (MULTI && !lastp) ? 31 : lane_last;
@@ -258,6 +277,10 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 #pragma unroll
     for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
     uint2 sc_next = make_uint2(0u, 0u);
+    if (WAVE && !first && X > 0) {
+        if (lane0) while ((avail = ld_acquire_u32(prog_in)) < 1u) {}
+        avail = __shfl_sync(0xffffffffu, avail, 0);
+    }
     if (MULTI && !first && lane0 && X > 0) sc_next = scratch[0];
 
     // one step; HO = previous row, HN = this row
@@ -289,7 +312,10 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         }                                                                                         \
         if (MULTI && !lastp && lane == 31) {                                                      \
             const uint32_t pos = (S)-31u; /* wraps for S < 31 -> fails the bound test */          \
-            if (pos < X) scratch[pos] = make_uint2((uint32_t)oh, (uint32_t)oe);                   \
+            if (pos < X) {                                                                        \
+                scratch_out[pos] = make_uint2((uint32_t)oh, (uint32_t)oe);                        \
+                if (WAVE && ((pos & 31u) == 31u || pos + 1u == X)) st_release_u32(prog_out, pos + 1u); \
+            }                                                                                     \
         }
 #define BSA_STEP_FAST(HO, HN, B, S) { BSA_STEP_CORE(HO, HN, B, S) }
 #define BSA_STEP(HO, HN, B, S)                                                                    \
@@ -316,6 +342,14 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     }
 
     for (uint32_t s = 0; s < nsteps; s += U) {
+        if (WAVE && !first) {
+            // this group prefetches boundary entries up to index s + U
+            const uint32_t need = s + U + 1u < X ? s + U + 1u : X;
+            if (avail < need) {
+                if (lane0) while ((avail = ld_acquire_u32(prog_in)) < need) {}
+                avail = __shfl_sync(0xffffffffu, avail, 0);
+            }
+        }
         uint32_t any = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -377,8 +411,8 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift) {
 template <int K>
 struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= 12 ? 3 : 2); };
 
-constexpr uint32_t kChunkResidues = 3072;   // stream residues per chunk (fill/drain is 31 steps)
-constexpr uint32_t kMaxChunks = 256;
+constexpr uint32_t kChunkBig = 4096;    // stream residues per chunk (pipeline fill is 31 steps)
+constexpr uint32_t kChunkSmall = 640;
 
 template <int K, bool MULTI>
 __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_kernel(const KArgs a) {
@@ -402,10 +436,15 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
         const uint8_t* tc = a.T.codes + t0;
         const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift);
 
+        // chunk schedule: big chunks over the first 13/16 of the stream, small ones over the rest,
+        // so the warps reach the item's closing barrier within half a small chunk of each other
         const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
         const uint64_t span = x1 - x0;
-        uint32_t nch = (uint32_t)((span + kChunkResidues - 1) / kChunkResidues);
-        nch = nch < (uint32_t)kWarpsPerCta ? (uint32_t)kWarpsPerCta : (nch > kMaxChunks ? kMaxChunks : nch);
+        const uint64_t head = span - span * 3 / 16;
+        const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
+        uint32_t nsmall = (uint32_t)((span - head + kChunkSmall - 1) / kChunkSmall);
+        if (nsmall < (uint32_t)kWarpsPerCta) nsmall = kWarpsPerCta;
+        const uint32_t nch = nbig + nsmall;
         const uint32_t npass = MULTI ? (m + 32 * K - 1) / (32 * K) : 1u;
         // MULTI: the boundary column of the whole item, addressed by stream position
         uint2* scratch = MULTI ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : nullptr;
@@ -427,11 +466,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c >= nch) break;
                 // chunk c = the queries whose first residue falls in its share of the stream
-                const uint32_t qa = c == 0 ? it.q_begin
-                                           : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + span * c / nch);
+                const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
+                const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig
+                                                  : head + (span - head) * (c + 1 - nbig) / nsmall;
+                const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
                 const uint32_t qb = c + 1 == nch ? it.q_end
-                                                 : lower_bound_off(a.Q.off, it.q_begin, it.q_end,
-                                                                   x0 + span * (c + 1) / nch);
+                                                 : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
                 const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
                 if (g1 > g0)
                     stream_block<K, false, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
@@ -497,6 +537,87 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
     }
 }
 
+
+// K3 -- intra-task wavefront for long pairs.  Every WARP is an independent worker with its own
+// profile slice in shared memory; work items are (pair, column block) claimed in dependency
+// order from a global counter, so the block to the left of a claimed item is always already
+// running (or done) and the spin-wait on its progress counter cannot deadlock.  The column
+// blocks of one pair thus sweep the DP matrix as a staggered wavefront over many SMs.
+constexpr int kWaveK = 8;        // 256 columns per block
+constexpr int kWaveWarps = 8;
+
+__global__ void __launch_bounds__(kWaveWarps * 32) gotoh_wave_kernel(const KArgs a) {
+    extern __shared__ uint4 smem[];
+    constexpr int K = kWaveK;
+    constexpr int ROW = KTraits<K>::ROW;
+    constexpr int W = KTraits<K>::W;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int C = a.C;
+    uint4* prof = smem + (size_t)warp * (C + 2) * ROW;
+    uint4* rsH = prof + (size_t)C * ROW;
+    uint4* rsF = rsH + ROW;
+    const Consts cs = make_consts<K>(a.go, a.ge, 0);
+    const int S = 4, P3 = 3;
+
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(a.item_counter, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= a.n_items) break;
+        const uint2 item = a.wave_items[wi];
+        const PairRec pr = a.pairs[item.x];
+        const uint32_t pass = item.y;
+        const uint64_t t0 = a.T.off[pr.t];
+        const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - t0);
+        const uint8_t* tc = a.T.codes + t0;
+        const uint32_t npass = (m + 32 * K - 1) / (32 * K);
+        const uint32_t colbase = pass * 32 * K;
+        const uint64_t g0 = a.Q.off[pr.q], g1 = a.Q.off[pr.q + 1];
+        const uint32_t n = (uint32_t)(g1 - g0);
+
+        // warp-private profile of this column block (same layout as build_profile)
+        __syncwarp();
+        for (int idx = lane; idx < C * ROW; idx += 32) {
+            const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
+            int o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * v + e;
+                const uint32_t col = colbase + ln * K + c;
+                o[e] = (c < K && col < m) ? (int)a.subst[code * C + (tc[col] & kCodeMask)] * S + P3 : cs.T_PAD;
+            }
+            prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        for (int r = lane; r < ROW; r += 32) {
+            const int v = r >> 5, ln = r & 31;
+            int h[4], f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long j = (long long)colbase + ln * K + 4 * v + e + 1;
+                h[e] = (int)((a.go + (j - 1) * a.ge) * S);
+                f[e] = h[e] + cs.GO;
+            }
+            rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
+            rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
+        }
+        __syncwarp();
+
+        const bool lastp = (pass + 1 == npass);
+        const int lane_last = (int)((m - 1 - colbase) / K);
+        const int slot_last = (int)((m - 1 - colbase) % K);
+        const long long jl = (long long)colbase + (long long)lane * K;
+        const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * S);
+        uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 32) * 32 * W;
+        uint2* bnd = a.scratch + pr.scr_off;          // (npass - 1) boundary columns of n entries
+        uint32_t* prog = a.progress + pr.prog_off;
+        stream_block<K, true, true, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
+                                          lastp ? lane_last : 31, slot_last, hdiag0, cs, a.one,
+                                          pass ? bnd + (size_t)(pass - 1) * n : nullptr, a.scores, nullptr,
+                                          pr.out, dirs, lastp ? nullptr : bnd + (size_t)pass * n,
+                                          pass ? prog + (pass - 1) : nullptr, lastp ? nullptr : prog + pass);
+    }
+}
 
 // Walks the stored directions exactly as GlobalAligner::backtrace does
 // (global.rs:146-201): state H follows diag > E > F, state E/F keeps going while the

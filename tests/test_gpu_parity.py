@@ -171,6 +171,25 @@ def test_long_templates_multipass_and_traceback(ctx, oracle_matrices):
         assert one["score"] == s[k] and one["n_identical"] == n2[k] and one["path"] == paths[k].decode()
 
 
+def test_titin_scale_pair_wavefront(ctx, oracle_matrices):
+    """BASELINE configs[4]: a 21k x 26k pair (and its transpose) through the K3 wavefront with
+    full traceback; the oracle needs 3 x 26001^2 bytes, so only two pairs."""
+    res, off = synth.generate(3, seed=1006, dist=0, lo=21000, hi=26000)
+    ctx.set_scoring("BLOSUM62", -10, -1)
+    ctx.load_sequences(0, res, off)
+    qi, ti = np.array([0, 2, 1]), np.array([1, 0, 1])
+    s, nid, paths = ctx.align_pairs_paths(0, 0, qi, ti)
+    raw = res.tobytes()
+    M = oracle_matrices["BLOSUM62"]
+    for k in range(3):
+        q = raw[int(off[qi[k]]):int(off[qi[k] + 1])]
+        t = raw[int(off[ti[k]]):int(off[ti[k] + 1])]
+        one = c_oracle.align_pair(q, t, M[0], M[1], -10, -1)
+        assert one["score"] == s[k] and one["n_identical"] == nid[k]
+        assert one["path"] == paths[k].decode()
+    assert nid[2] == len(raw[int(off[1]):int(off[2])])      # self alignment: 100 % identical
+
+
 def test_range_fallback_uses_direction_path(ctx, oracle_matrices):
     """Sequences whose score range does not fit the packed lanes go through the
     direction-store kernels and still match (7k residues with BLOSUM62 exceeds 2^16)."""
