@@ -7,3 +7,4 @@ from .alignment import (AlignmentReporter, AlignmentStatistics, CollectReporter,
                         aligned_sequences, aligned_strings, aligned_symbols, triangle_counts)
 from .scoring import SubstitutionMatrix, SubstitutionMatrixList, ncbi_text  # noqa: F401
 from .sequence import Sequence, count_identical, len_ungapped, pack, ungapped_lengths  # noqa: F401
+from . import clustering  # noqa: F401,E402

@@ -13,13 +13,14 @@ LIB_PATH = os.path.join(_HERE, "libbioshell_align.so")
 OK = 0
 ERRORS = {-1: "BAD_ARG", -2: "UNSUPPORTED_GAPS", -3: "RANGE", -4: "CUDA", -5: "OOM", -6: "FORMAT",
           -7: "ALPHABET", -8: "EMPTY"}
-WANT_SCORE, WANT_IDENTICAL, OUT_DEVICE = 1, 2, 4
+WANT_SCORE, WANT_IDENTICAL, OUT_DEVICE, IN_DEVICE = 1, 2, 4, 8
 
 # every symbol include/bioshell_align.h declares
 SYMBOLS = ["bsa_device_count", "bsa_create", "bsa_destroy", "bsa_last_error",
            "bsa_parse_ncbi_matrix", "bsa_set_scoring", "bsa_load_sequences", "bsa_align_all_pairs",
            "bsa_all_vs_all", "bsa_one_vs_many", "bsa_plan_shards", "bsa_align_pairs_paths",
-           "bsa_host_alloc_pinned", "bsa_host_free_pinned", "bsa_get_stats", "bsa_measure_int_peak"]
+           "bsa_host_alloc_pinned", "bsa_host_free_pinned", "bsa_get_stats", "bsa_measure_int_peak",
+           "bsa_hclust"]
 
 
 class BsaError(RuntimeError):
@@ -66,6 +67,7 @@ def lib():
     L.bsa_one_vs_many.argtypes = [vp, C.c_int, C.c_int, u32, vp, vp]
     L.bsa_plan_shards.argtypes = [vp, C.c_int, C.c_int, vp, u32, vp]
     L.bsa_align_pairs_paths.argtypes = [vp, C.c_int, C.c_int, vp, vp, u64, vp, vp, vp, vp]
+    L.bsa_hclust.argtypes = [vp, u32, vp, C.c_int, u32, vp, vp, vp]
     L.bsa_host_alloc_pinned.argtypes = [C.c_size_t]
     L.bsa_host_alloc_pinned.restype = vp
     L.bsa_host_free_pinned.argtypes = [vp]

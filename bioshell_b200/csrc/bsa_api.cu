@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gotoh_kernels.cuh"
+#include "hclust_kernels.cuh"
 #include "int_peak.cuh"
 
 using namespace bsa;
@@ -98,7 +99,7 @@ struct bsa_ctx {
     SeqSet sets[kMaxSets];
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
-        raw, lut, presence, progress, wave_items;
+        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux;
     bsa_stats stats;
 };
 
@@ -477,7 +478,7 @@ void bsa_destroy(bsa_ctx* c) {
     for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
-                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items};
+                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -1018,6 +1019,68 @@ int bsa_align_pairs_paths(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
     ctx->stats.kernel_ms = ms;
     ctx->stats.total_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return BSA_OK;
+}
+
+// hierarchical_clustering (bioshell-clustering/src/hierarchical/hierarchical.rs:22-80)
+int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_t flags, uint32_t* mat_i,
+               uint32_t* mat_j, float* merge_dist) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    if (n == 0 || !dist || linkage < 0 || linkage > 5) return fail(ctx, BSA_ERR_BAD_ARG, "bad argument");
+    const auto wall0 = std::chrono::steady_clock::now();
+    CK(cudaSetDevice(ctx->device));
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    cudaStream_t st = ctx->streams[0];
+    const size_t nn = (size_t)n * n;
+    const uint32_t grid = (uint32_t)ctx->sms * 4;
+    CK(ctx->hc_matrix.ensure(nn * sizeof(float)));
+    // aux: rmap[n] sizes[n] order[2] mat_i[n] mat_j[n] mdist[n] result[n] partial[grid]
+    const size_t aux_bytes = (size_t)n * 4 * 6 + 16 + (size_t)grid * sizeof(HcBest) + 64;
+    CK(ctx->hc_aux.ensure(aux_bytes));
+    HcState hs;
+    hs.D = ctx->hc_matrix.as<float>();
+    uint8_t* a = ctx->hc_aux.as<uint8_t>();
+    hs.rmap = (uint32_t*)a; a += (size_t)n * 4;
+    hs.sizes = (uint32_t*)a; a += (size_t)n * 4;
+    hs.mat_i = (uint32_t*)a; a += (size_t)n * 4;
+    hs.mat_j = (uint32_t*)a; a += (size_t)n * 4;
+    hs.mdist = (float*)a; a += (size_t)n * 4;
+    hs.result = (float*)a; a += (size_t)n * 4;
+    hs.order = (uint32_t*)a; a += 16;
+    hs.partial = (HcBest*)a;
+    hs.n = n;
+    hs.rule = linkage;
+    CK(cudaMemcpyAsync(hs.D, dist, nn * sizeof(float),
+                       (flags & BSA_IN_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!(flags & BSA_IN_DEVICE)) ctx->stats.h2d_bytes += nn * sizeof(float);
+    CK(cudaEventRecord(ctx->ev_start, st));
+    hclust_init_kernel<<<grid, 256, 0, st>>>(hs);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    for (uint32_t step = 0; step + 1 < n; ++step) {
+        hclust_argmin_kernel<<<grid, 256, 0, st>>>(hs);
+        hclust_merge_kernel<<<1, 1024, 0, st>>>(hs, grid);
+        ctx->stats.launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_end, st));
+    uint32_t fin[2] = {0, 0};
+    CK(cudaMemcpyAsync(fin, hs.order, 8, cudaMemcpyDeviceToHost, st));
+    if (n > 1) {
+        if (mat_i) CK(cudaMemcpyAsync(mat_i, hs.mat_i, (size_t)(n - 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (mat_j) CK(cudaMemcpyAsync(mat_j, hs.mat_j, (size_t)(n - 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (merge_dist) CK(cudaMemcpyAsync(merge_dist, hs.mdist, (size_t)(n - 1) * 4, cudaMemcpyDeviceToHost, st));
+        ctx->stats.d2h_bytes += (size_t)(n - 1) * 12;
+    }
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));
+    ctx->stats.kernel_ms = ms;
+    ctx->stats.pairs = n > 1 ? n - 1 : 0;
+    ctx->stats.total_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    if (fin[1] & 0x80000000u)
+        return fail(ctx, BSA_ERR_RANGE, "no finite distance left to merge (the reference panics here)");
     return BSA_OK;
 }
 

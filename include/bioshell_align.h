@@ -25,6 +25,10 @@
  *                          bioshell-seq/examples/needleman_wunsh.rs:108-109
  *   bsa_align_pairs_paths  GlobalAligner::align + backtrace -> AlignmentPath
  *                          (global.rs:57-201, alignment_path.rs:34-48,107-115)
+ *   bsa_hclust             hierarchical_clustering + HierarchicalClusteringMatrix (the consumer
+ *                          of the identity matrix)
+ *                          bioshell-clustering/src/hierarchical/hierarchical.rs:22-80,
+ *                          clustering_matrix.rs:11-74, strategies/mod.rs:25-92
  *
  * Conventions: plain pointers and sizes only.  The caller allocates every input
  * and output buffer and keeps it alive for the duration of the call; the library
@@ -62,6 +66,7 @@ extern "C" {
 #define BSA_WANT_SCORE 1u
 #define BSA_WANT_IDENTICAL 2u
 #define BSA_OUT_DEVICE 4u /* output pointers are device pointers on the context's GPU */
+#define BSA_IN_DEVICE 8u  /* input matrix pointer is a device pointer (bsa_hclust) */
 
 typedef struct bsa_ctx bsa_ctx;
 
@@ -139,6 +144,19 @@ int bsa_plan_shards(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_counts
 int bsa_align_pairs_paths(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_idx,
                           const uint32_t *t_idx, uint64_t n_pairs, int32_t *scores,
                           uint32_t *n_identical, uint8_t *path_buf, uint64_t *path_off);
+
+/*
+ * Hierarchical agglomerative clustering with the reference's exact merge order.
+ * dist: n x n row-major f32 of which ONLY dist[i*n+j] with i > j is read (as
+ * HierarchicalClusteringMatrix::new does, clustering_matrix.rs:14-19) and mirrored.
+ * linkage: 0 single, 1 complete, 2 average, 3 median, 4 centroid, 5 Ward
+ * (strategies/mod.rs:25-92).  Output, one entry per merge step s = 0..n-2:
+ * mat_i[s] < mat_j[s] = the matrix indices closest_elements returned, merge_dist[s] = their
+ * distance; the tree is rebuilt from them on the host (hierarchical.rs:44-75).
+ * flags: BSA_IN_DEVICE if dist is a device pointer.
+ */
+int bsa_hclust(bsa_ctx *ctx, uint32_t n, const float *dist, int linkage, uint32_t flags,
+               uint32_t *mat_i, uint32_t *mat_j, float *merge_dist);
 
 /* Pinned host memory so device->host result copies run at full PCIe rate. */
 void *bsa_host_alloc_pinned(size_t bytes);

@@ -26,8 +26,8 @@ class _SeqSet(C.Structure):
 
 def build(force=False):
     """Compile the C restatement with the committed recipe (oracle/Makefile)."""
-    src = os.path.join(_HERE, "bioshell_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("bioshell_oracle.c", "hclust_oracle.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -67,6 +67,8 @@ def lib():
                                            C.c_void_p, C.POINTER(C.c_uint64),
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.orc_expand_and_count.restype = C.c_int
+        L.orc_hclust.argtypes = [C.c_uint32, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.orc_hclust.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -193,3 +195,21 @@ def align_pair_list(Q, T, score, aa_index, go, ge, pq, pt, lmax, n_threads=1, cl
     if rc:
         raise OracleError(rc)
     return dict(score=sc, n_identical=nid, cells=cells.value)
+
+
+LINKAGE = {"single": 0, "complete": 1, "average": 2, "median": 3, "centroid": 4, "ward": 5}
+
+
+def hclust(dist, rule):
+    """hierarchical_clustering (bioshell-clustering/src/hierarchical/hierarchical.rs:22-80) on a full
+    n x n f32 matrix of which only [i][j], i > j is read.  Returns the merge log."""
+    d = np.ascontiguousarray(dist, np.float32)
+    n = d.shape[0]
+    out = dict(mat_i=np.zeros(max(n - 1, 1), np.uint32), mat_j=np.zeros(max(n - 1, 1), np.uint32),
+               id_i=np.zeros(max(n - 1, 1), np.uint32), id_j=np.zeros(max(n - 1, 1), np.uint32),
+               dist=np.zeros(max(n - 1, 1), np.float32))
+    rc = lib().orc_hclust(n, _ptr(d), LINKAGE[rule] if isinstance(rule, str) else int(rule), _ptr(out["mat_i"]),
+                          _ptr(out["mat_j"]), _ptr(out["id_i"]), _ptr(out["id_j"]), _ptr(out["dist"]))
+    if rc < 0:
+        raise OracleError(int(rc))
+    return {k: v[:rc] for k, v in out.items()}
