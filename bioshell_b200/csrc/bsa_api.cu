@@ -1032,8 +1032,9 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     cudaStream_t st = ctx->streams[0];
     const size_t nn = (size_t)n * n;
-    const uint32_t grid = (uint32_t)ctx->sms * 4;
-    CK(ctx->hc_matrix.ensure(nn * sizeof(float)));
+    const uint32_t grid = (uint32_t)ctx->sms * 8;
+    const uint32_t pitch = (n + 31u) & ~31u;
+    CK(ctx->hc_matrix.ensure((size_t)n * pitch * sizeof(float)));
     // aux: rmap[n] sizes[n] order[2] mat_i[n] mat_j[n] mdist[n] result[n] partial[grid]
     const size_t aux_bytes = (size_t)n * 4 * 6 + 16 + (size_t)grid * sizeof(HcBest) + 64;
     CK(ctx->hc_aux.ensure(aux_bytes));
@@ -1047,19 +1048,26 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     hs.mdist = (float*)a; a += (size_t)n * 4;
     hs.result = (float*)a; a += (size_t)n * 4;
     hs.order = (uint32_t*)a; a += 16;
+    uint32_t* done_counter = hs.order + 2;
     hs.partial = (HcBest*)a;
     hs.n = n;
+    hs.pitch = pitch;
     hs.rule = linkage;
-    CK(cudaMemcpyAsync(hs.D, dist, nn * sizeof(float),
-                       (flags & BSA_IN_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (!(flags & BSA_IN_DEVICE)) ctx->stats.h2d_bytes += nn * sizeof(float);
+    const float* d_in = dist;
+    if (!(flags & BSA_IN_DEVICE)) {
+        CK(ctx->raw.ensure(nn * sizeof(float)));
+        CK(cudaMemcpyAsync(ctx->raw.p, dist, nn * sizeof(float), cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += nn * sizeof(float);
+        d_in = ctx->raw.as<float>();
+    }
     CK(cudaEventRecord(ctx->ev_start, st));
-    hclust_init_kernel<<<grid, 256, 0, st>>>(hs);
+    hclust_init_kernel<<<grid, 256, 0, st>>>(hs, d_in);
     CK(cudaGetLastError());
     ctx->stats.launches++;
+    const uint32_t merge_grid = std::max(1u, std::min(24u, (n + 255u) / 256u));
     for (uint32_t step = 0; step + 1 < n; ++step) {
         hclust_argmin_kernel<<<grid, 256, 0, st>>>(hs);
-        hclust_merge_kernel<<<1, 1024, 0, st>>>(hs, grid);
+        hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, grid, done_counter);
         ctx->stats.launches += 2;
     }
     CK(cudaGetLastError());

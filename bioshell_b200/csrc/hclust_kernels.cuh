@@ -38,6 +38,7 @@ struct HcState {
     uint32_t* mat_j;
     float* mdist;
     uint32_t n;
+    uint32_t pitch;      // floats per physical row (multiple of 32: rows are 128-byte aligned)
     int rule;
 };
 
@@ -73,56 +74,101 @@ __device__ __forceinline__ float hc_rule(int rule, uint32_t si, uint32_t sj, uin
 }
 
 // HierarchicalClusteringMatrix::new (clustering_matrix.rs:11-22): only in[i][j], i > j is read
-__global__ void hclust_init_kernel(HcState s) {
+__global__ void hclust_init_kernel(HcState s, const float* __restrict__ in) {
     const uint32_t n = s.n;
-    const size_t total = (size_t)n * n;
+    const size_t total = (size_t)n * s.pitch;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t i = (uint32_t)(idx / n), j = (uint32_t)(idx - (size_t)i * n);
-        if (i < j) s.D[idx] = s.D[(size_t)j * n + i];   // mirror the lower triangle upwards
-        else if (i == j) s.D[idx] = 0.0f;
+        const uint32_t i = (uint32_t)(idx / s.pitch), j = (uint32_t)(idx - (size_t)i * s.pitch);
+        float v = 0.0f;
+        if (j < n && i != j) v = i > j ? in[(size_t)i * n + j] : in[(size_t)j * n + i];   // mirror the lower triangle
+        s.D[idx] = v;
     }
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         s.rmap[k] = k;
         s.sizes[k] = 1;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { s.order[0] = n; s.order[1] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { s.order[0] = n; s.order[1] = 0; s.order[2] = 0; }
 }
 
-// closest_elements (clustering_matrix.rs:27-42): rows are dealt round-robin over the CTAs
+// closest_elements (clustering_matrix.rs:27-42).  HBM-bound: every warp takes whole rows
+// (round-robin), reads the part right of the diagonal with 16-byte loads, four of them in
+// flight per lane, and keeps the lexicographic (value, j, i) minimum.
+__device__ __forceinline__ void hc_consider(float v, uint32_t j, uint32_t i, HcBest& b) {
+    // the reference starts from f32::MAX with a strict `<`: MAX itself never wins
+    if (v < FLT_MAX && hc_better(v, j, i, b)) b = HcBest{v, j, i};
+}
+
 __global__ void __launch_bounds__(256) hclust_argmin_kernel(HcState s) {
     const uint32_t order = s.order[0];
-    HcBest best{FLT_MAX, 0u, 0u};
-    bool have = false;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    HcBest best{FLT_MAX, 0xffffffffu, 0xffffffffu};
     if (order >= 2) {
-        for (uint32_t i = blockIdx.x; i + 1 < order; i += gridDim.x) {
-            const float* row = s.D + (size_t)s.rmap[i] * s.n;
-            for (uint32_t j = i + 1 + threadIdx.x; j < order; j += blockDim.x) {
-                const float v = row[j];
-                // the reference starts from f32::MAX with a strict `<`: MAX itself never wins
-                if (v < FLT_MAX && (!have || hc_better(v, j, i, best))) { best = HcBest{v, j, i}; have = true; }
+        for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp; i + 1 < order; i += nwarps) {
+            const float* row = s.D + (size_t)s.rmap[i] * s.pitch;
+            const uint32_t j0 = i + 1;
+            const uint32_t ja = (j0 + 3u) & ~3u;                  // first 16-byte aligned column
+            const uint32_t jb = order & ~3u;                      // end of the aligned body
+            if (ja >= jb) {
+                for (uint32_t j = j0 + lane; j < order; j += 32) hc_consider(row[j], j, i, best);
+                continue;
+            }
+            if (j0 + lane < ja) hc_consider(row[j0 + lane], j0 + lane, i, best);
+            if (jb + lane < order) hc_consider(row[jb + lane], jb + lane, i, best);
+            const float4* r4 = reinterpret_cast<const float4*>(row);
+            uint32_t q = (ja >> 2) + lane;
+            const uint32_t qe = jb >> 2;
+            for (; q + 96 < qe; q += 128) {
+                const float4 a = r4[q], b = r4[q + 32], c = r4[q + 64], d = r4[q + 96];
+                const float4 v[4] = {a, b, c, d};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = (q + 32 * u) << 2;
+                    hc_consider(v[u].x, j, i, best); hc_consider(v[u].y, j + 1, i, best);
+                    hc_consider(v[u].z, j + 2, i, best); hc_consider(v[u].w, j + 3, i, best);
+                }
+            }
+            for (; q < qe; q += 32) {
+                const float4 a = r4[q];
+                const uint32_t j = q << 2;
+                hc_consider(a.x, j, i, best); hc_consider(a.y, j + 1, i, best);
+                hc_consider(a.z, j + 2, i, best); hc_consider(a.w, j + 3, i, best);
             }
         }
     }
-    if (!have) best = HcBest{FLT_MAX, 0xffffffffu, 0xffffffffu};
-    // block reduction
-    __shared__ HcBest sm[256];
-    sm[threadIdx.x] = best;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) {
-            const HcBest o = sm[threadIdx.x + off];
-            if (hc_better(o.v, o.j, o.i, sm[threadIdx.x])) sm[threadIdx.x] = o;
-        }
-        __syncthreads();
+    // warp, then block reduction
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        HcBest o;
+        o.v = __shfl_down_sync(0xffffffffu, best.v, off);
+        o.j = __shfl_down_sync(0xffffffffu, best.j, off);
+        o.i = __shfl_down_sync(0xffffffffu, best.i, off);
+        if (hc_better(o.v, o.j, o.i, best)) best = o;
     }
-    if (threadIdx.x == 0) s.partial[blockIdx.x] = sm[0];
+    __shared__ HcBest sm[8];
+    if (lane == 0) sm[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        HcBest b = sm[0];
+        for (uint32_t w = 1; w < (blockDim.x >> 5); ++w)
+            if (hc_better(sm[w].v, sm[w].j, sm[w].i, b)) b = sm[w];
+        s.partial[blockIdx.x] = b;
+    }
 }
 
-__global__ void __launch_bounds__(1024) hclust_merge_kernel(HcState s, uint32_t n_partial) {
-    __shared__ HcBest sm[1024];
-    __shared__ uint32_t sh_i, sh_j, sh_order;
-    const uint32_t tid = threadIdx.x;
+// One merge: update_distances(i, j, rule, i) + replace_with_last(j) + bookkeeping
+// (clustering_matrix.rs:47-74, hierarchical.rs:44-75), on several CTAs with no barrier between
+// them.  Every CTA re-reduces the argmin partials to (i, j); thread k then owns element k of the
+// new row: it computes rule(..., D[i][k], D[j][k]), writes D[i][k] and D[k][i], and performs the
+// column copy of replace_with_last for row k.  The reference computes all results before it
+// writes any; here the only elements another thread could clobber first are k = i and k = j,
+// whose inputs are known without reading (the diagonal is 0 and the live matrix is symmetric,
+// so D[j][i] = D[i][j] = dij).  The last CTA to finish does the scalar bookkeeping.
+__global__ void __launch_bounds__(256) hclust_merge_kernel(HcState s, uint32_t n_partial, uint32_t* done_counter) {
+    __shared__ HcBest sm[8];
+    __shared__ uint32_t sh_i, sh_j, sh_ticket;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t order = s.order[0];
     if (order < 2) return;
     HcBest best{FLT_MAX, 0xffffffffu, 0xffffffffu};
@@ -130,67 +176,78 @@ __global__ void __launch_bounds__(1024) hclust_merge_kernel(HcState s, uint32_t 
         const HcBest o = s.partial[p];
         if (hc_better(o.v, o.j, o.i, best)) best = o;
     }
-    sm[tid] = best;
-    __syncthreads();
-    for (int off = 512; off > 0; off >>= 1) {
-        if ((int)tid < off) {
-            const HcBest o = sm[tid + off];
-            if (hc_better(o.v, o.j, o.i, sm[tid])) sm[tid] = o;
-        }
-        __syncthreads();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        HcBest o;
+        o.v = __shfl_down_sync(0xffffffffu, best.v, off);
+        o.j = __shfl_down_sync(0xffffffffu, best.j, off);
+        o.i = __shfl_down_sync(0xffffffffu, best.i, off);
+        if (hc_better(o.v, o.j, o.i, best)) best = o;
     }
+    if (lane == 0) sm[warp] = best;
+    __syncthreads();
     if (tid == 0) {
         HcBest b = sm[0];
+        for (uint32_t w = 1; w < (blockDim.x >> 5); ++w)
+            if (hc_better(sm[w].v, sm[w].j, sm[w].i, b)) b = sm[w];
         if (b.j == 0xffffffffu) { b.i = 0; b.j = 0; }   // nothing below f32::MAX: the reference returns (0,0)
-        sh_i = b.i; sh_j = b.j; sh_order = order;
+        sh_i = b.i; sh_j = b.j;
     }
     __syncthreads();
     const uint32_t i = sh_i, j = sh_j;
-    const uint32_t n = s.n;
-    if (i == j) {   // the reference panics here (clusters.remove(&j)); stop and let the host report it
-        if (tid == 0) { s.order[0] = 0; s.order[1] |= 0x80000000u; }
-        return;
-    }
-    float* row_i = s.D + (size_t)s.rmap[i] * n;
-    const float* row_j = s.D + (size_t)s.rmap[j] * n;
-    const float dij = row_i[j];
-    const uint32_t si = s.sizes[i], sj = s.sizes[j];
-    const uint32_t step = s.order[1];
-    // update_distances(i, j, rule, i): all results first (clustering_matrix.rs:64-67) ...
-    for (uint32_t k = tid; k < order; k += blockDim.x)
-        s.result[k] = hc_rule(s.rule, si, sj, s.sizes[j], dij, row_i[k], row_j[k]);
-    __syncthreads();
-    // ... then row i and column i (clustering_matrix.rs:68-71)
-    for (uint32_t k = tid; k < order; k += blockDim.x) {
-        const float r = s.result[k];
-        row_i[k] = r;
-        s.D[(size_t)s.rmap[k] * n + i] = r;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        row_i[i] = 0.0f;                      // clustering_matrix.rs:72
-        s.sizes[i] = sj + si;                 // :73
-        s.mat_i[step] = i;
-        s.mat_j[step] = j;
-        s.mdist[step] = dij;
-    }
+    const uint32_t pitch = s.pitch;
     const uint32_t last = order - 1;
-    if (j < last) {
-        // replace_with_last(j) (clustering_matrix.rs:47-53): swap the ROWS, copy the column
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t t = s.rmap[j];
-            s.rmap[j] = s.rmap[last];
-            s.rmap[last] = t;
-        }
-        __syncthreads();
-        for (uint32_t r = tid; r < last; r += blockDim.x) {
-            float* row = s.D + (size_t)s.rmap[r] * n;
-            row[j] = row[last];
+    const bool bad = (i == j);   // the reference panics here (clusters.remove(&j))
+    const uint32_t step = s.order[1];
+    float dij = 0.0f;
+    if (!bad) {
+        const uint32_t ri = s.rmap[i], rj = s.rmap[j], rl = s.rmap[last];
+        float* row_i = s.D + (size_t)ri * pitch;
+        const float* row_j = s.D + (size_t)rj * pitch;
+        dij = row_i[j];
+        const uint32_t si = s.sizes[i], sj = s.sizes[j], sk = s.sizes[j];   // sizes[j] as size_k: clustering_matrix.rs:66
+        const bool moved = j < last;                                        // replace_with_last(j) follows
+        for (uint32_t k = blockIdx.x * blockDim.x + tid; k < order; k += gridDim.x * blockDim.x) {
+            const float dik = k == i ? 0.0f : (k == j ? dij : row_i[k]);
+            const float djk = k == j ? 0.0f : (k == i ? dij : row_j[k]);
+            float r = hc_rule(s.rule, si, sj, sk, dij, dik, djk);
+            const uint32_t rk = k == i ? ri : (k == j ? rj : (k == last ? rl : s.rmap[k]));
+            float* row_k = s.D + (size_t)rk * pitch;
+            if (k == i) r = 0.0f;                              // matrix[new_index][new_index] = 0.0 (:72)
+            if (!(moved && k == j)) row_i[k] = r;              // (k == j: the column copy below overwrites it)
+            row_k[i] = r;
+            if (moved) {
+                // replace_with_last(j): logical row j becomes the old last row; column j <- column last
+                if (k == last) {
+                    row_i[j] = r;                              // row i: its new [last] entry is this r
+                } else if (k == j) {
+                    float* nr = s.D + (size_t)rl * pitch;      // the row that moves into slot j
+                    nr[j] = nr[last];
+                } else if (k != i) {
+                    row_k[j] = row_k[last];
+                }
+            }
         }
     }
+    // the last CTA to get here owns the scalars (all others have finished reading them)
+    __threadfence();
     __syncthreads();
-    if (tid == 0) { s.order[0] = last; s.order[1] = step + 1; }
+    if (tid == 0) sh_ticket = atomicAdd(done_counter, 1u);
+    __syncthreads();
+    if (sh_ticket != gridDim.x - 1 || tid != 0) return;
+    *done_counter = 0;
+    if (bad) { s.order[0] = 0; s.order[1] |= 0x80000000u; return; }
+    s.sizes[i] = s.sizes[j] + s.sizes[i];                      // :73
+    s.mat_i[step] = i;
+    s.mat_j[step] = j;
+    s.mdist[step] = dij;
+    if (j < last) {
+        const uint32_t t = s.rmap[j];
+        s.rmap[j] = s.rmap[last];
+        s.rmap[last] = t;
+    }
+    s.order[0] = last;
+    s.order[1] = step + 1;
 }
 
 }  // namespace bsa
