@@ -1064,7 +1064,8 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     hclust_init_kernel<<<grid, 256, 0, st>>>(hs, d_in);
     CK(cudaGetLastError());
     ctx->stats.launches++;
-    const uint32_t merge_grid = std::max(1u, std::min(24u, (n + 255u) / 256u));
+    uint32_t merge_grid = std::max(1u, std::min(24u, (n + 255u) / 256u));
+    if (const char* e = getenv("BSA_HC_MERGE_GRID")) merge_grid = (uint32_t)std::max(1, atoi(e));   // debugging aid
     for (uint32_t step = 0; step + 1 < n; ++step) {
         hclust_argmin_kernel<<<grid, 256, 0, st>>>(hs);
         hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, grid, done_counter);

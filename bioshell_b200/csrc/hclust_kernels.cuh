@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) hclust_argmin_kernel(HcState s) {
 __global__ void __launch_bounds__(256) hclust_merge_kernel(HcState s, uint32_t n_partial, uint32_t* done_counter) {
     __shared__ HcBest sm[8];
     __shared__ uint32_t sh_i, sh_j, sh_ticket;
+    __shared__ float sh_v;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t order = s.order[0];
     if (order < 2) return;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256) hclust_merge_kernel(HcState s, uint32_t n
         for (uint32_t w = 1; w < (blockDim.x >> 5); ++w)
             if (hc_better(sm[w].v, sm[w].j, sm[w].i, b)) b = sm[w];
         if (b.j == 0xffffffffu) { b.i = 0; b.j = 0; }   // nothing below f32::MAX: the reference returns (0,0)
-        sh_i = b.i; sh_j = b.j;
+        sh_i = b.i; sh_j = b.j; sh_v = b.v;
     }
     __syncthreads();
     const uint32_t i = sh_i, j = sh_j;
@@ -199,12 +200,13 @@ __global__ void __launch_bounds__(256) hclust_merge_kernel(HcState s, uint32_t n
     const uint32_t last = order - 1;
     const bool bad = (i == j);   // the reference panics here (clusters.remove(&j))
     const uint32_t step = s.order[1];
-    float dij = 0.0f;
+    // D[i][j] is the minimum the scan found; it must NOT be re-read from memory here: another CTA's
+    // column copy may already have overwritten row i's entry j
+    const float dij = sh_v;
     if (!bad) {
         const uint32_t ri = s.rmap[i], rj = s.rmap[j], rl = s.rmap[last];
         float* row_i = s.D + (size_t)ri * pitch;
         const float* row_j = s.D + (size_t)rj * pitch;
-        dij = row_i[j];
         const uint32_t si = s.sizes[i], sj = s.sizes[j], sk = s.sizes[j];   // sizes[j] as size_k: clustering_matrix.rs:66
         const bool moved = j < last;                                        // replace_with_last(j) follows
         for (uint32_t k = blockIdx.x * blockDim.x + tid; k < order; k += gridDim.x * blockDim.x) {
