@@ -99,7 +99,7 @@ struct bsa_ctx {
     SeqSet sets[kMaxSets];
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
-        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux;
+        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16;
     bsa_stats stats;
 };
 
@@ -131,12 +131,16 @@ inline int bitlen(uint64_t x) {
 // ---------------- kernel tables ----------------
 typedef void (*KernelFn)(const KArgs);
 KernelFn g_stream_single[kKMax + 1], g_stream_multi[kKMax + 1], g_dirs[kKMax + 1];
+typedef void (*Kernel16Fn)(const KArgs16);
+Kernel16Fn g_score16_single[kKMax + 1], g_score16_multi[kKMax + 1];
 
 template <int K>
 struct Reg {
     static void run() {
         g_stream_single[K] = gotoh_stream_kernel<K, false>;
         g_stream_multi[K] = gotoh_stream_kernel<K, true>;
+        g_score16_single[K] = gotoh_score16_kernel<K, false>;
+        g_score16_multi[K] = gotoh_score16_kernel<K, true>;
         Reg<K - 1>::run();
     }
 };
@@ -478,7 +482,7 @@ void bsa_destroy(bsa_ctx* c) {
     for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
-                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux};
+                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -712,9 +716,69 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     double padded = 0.0;
     const int cs_cap = bitlen(Q.maxlen);
 
+    // ---- score-only requests: pairs of templates in 16-bit packed lanes (gotoh_score16_kernel) ----
+    struct Group16 { std::vector<Item16> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0; };
+    std::vector<Group16> groups16(2 * (kKMax + 1));
+    std::vector<uint8_t> done16((size_t)(t_end - t_begin), 0);
+    if (want_s && !want_i && Q.empties.empty() && !getenv("BSA_NO_S16")) {
+        struct Cand { uint32_t t, cnt; uint64_t m; int key; };
+        std::vector<Cand> cands;
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
+            const uint64_t m = T.len(t);
+            if (cnt == 0 || m == 0) continue;
+            const KChoice kc = choose_k(m, C);
+            if (kc.K < 1) continue;
+            // every DP value (incl. borders and E/F one step below them) must fit a signed 16-bit lane
+            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
+            const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
+                               (int64_t)std::max(-ctx->min_m, 0);
+            if (std::max(ub, lb) >= 32000) continue;
+            cands.push_back(Cand{t, cnt, m, kc.K + (kc.multi ? kKMax + 1 : 0) + (int)kc.npass * 256});
+        }
+        // partners must agree on columns per lane, number of column blocks and query count
+        std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+            if (a.key != b.key) return a.key < b.key;
+            if (a.cnt != b.cnt) return a.cnt < b.cnt;
+            return a.m < b.m;
+        });
+        for (size_t i = 0; i < cands.size();) {
+            const Cand& A = cands[i];
+            const bool pair = i + 1 < cands.size() && cands[i + 1].key == A.key && cands[i + 1].cnt == A.cnt;
+            const Cand* B = pair ? &cands[i + 1] : nullptr;
+            const KChoice kc = choose_k(A.m, C);
+            const uint64_t m_pad = 32ull * kc.K * kc.npass;
+            uint64_t xb = (uint64_t)std::max(1.0, 2.0 * target_cells / (double)m_pad);
+            xb = std::min<uint64_t>(xb, 1u << 18);
+            Group16& grp = groups16[kc.K + (kc.multi ? kKMax + 1 : 0)];
+            uint32_t q = 0;
+            while (q < A.cnt) {
+                const uint64_t lim_off = Q.off[q] + xb;
+                uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + A.cnt + 1, lim_off) -
+                                         Q.off.begin()) - 1;
+                q2 = std::min(std::max(q2, q + 1), A.cnt);
+                Item16 it;
+                it.tA = A.t; it.tB = B ? B->t : 0xffffffffu;
+                it.q_begin = q; it.q_end = q2;
+                it.outA = first[A.t - t_begin] + q;
+                it.outB = B ? first[B->t - t_begin] + q : 0;
+                grp.items.push_back(it);
+                const uint64_t x = Q.off[q2] - Q.off[q];
+                padded += (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad * (B ? 2.0 : 1.0);
+                grp.cells += (double)x * (double)(A.m + (B ? B->m : 0));
+                if (kc.multi) grp.stride = std::max(grp.stride, x + 64);
+                q = q2;
+            }
+            done16[A.t - t_begin] = 1;
+            if (B) done16[B->t - t_begin] = 1;
+            i += pair ? 2 : 1;
+        }
+    }
+
     for (uint32_t t = t_begin; t < t_end; ++t) {
         const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
         if (cnt == 0) continue;
+        if (done16[t - t_begin]) continue;
         const uint64_t m = T.len(t);
         const uint64_t kbase = first[t - t_begin];
         if (m == 0) {
@@ -801,8 +865,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     int n_groups = 0;
     for (auto& g : groups) { n_items += g.items.size(); n_groups += g.items.empty() ? 0 : 1; }
     ctx->stats.items = (uint32_t)n_items;
-    CK(ctx->counters.ensure(groups.size() * 4));
+    CK(ctx->counters.ensure(2 * groups.size() * 4));
     cudaStream_t s0 = ctx->streams[0];
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * groups.size() * 4, s0));
     if (n_items) {
         std::vector<Item> all;
         all.reserve(n_items);
@@ -817,7 +882,6 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         CK(ctx->items.ensure(all.size() * sizeof(Item)));
         CK(cudaMemcpyAsync(ctx->items.p, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice, s0));
         ctx->stats.h2d_bytes += all.size() * sizeof(Item);
-        CK(cudaMemsetAsync(ctx->counters.p, 0, groups.size() * 4, s0));
         // every CTA of every concurrently running MULTI kernel owns its own boundary slice
         uint64_t scr_total = 0;
         for (int g : gorder) {
@@ -883,6 +947,80 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         }
     } else {
         CK(cudaEventRecord(ctx->ev_start, s0));
+    }
+    // ---- 16-bit score-only groups (they follow on the same streams) ----
+    {
+        size_t n16 = 0;
+        for (auto& g : groups16) n16 += g.items.size();
+        if (n16) {
+            std::vector<Item16> all;
+            all.reserve(n16);
+            std::vector<size_t> goff(groups16.size(), 0);
+            std::vector<int> gorder;
+            for (int g = (int)groups16.size() - 1; g >= 0; --g) if (!groups16[g].items.empty()) gorder.push_back(g);
+            uint64_t scr_total = 0;
+            for (int g : gorder) {
+                goff[g] = all.size();
+                all.insert(all.end(), groups16[g].items.begin(), groups16[g].items.end());
+                if (g > kKMax) {
+                    const int K = g - (kKMax + 1);
+                    uint32_t grid = 0;
+                    rc = grid_for(ctx, (KernelFn)g_score16_multi[K], K, C, (uint32_t)groups16[g].items.size(), &grid);
+                    if (rc) return rc;
+                    groups16[g].scr_off = scr_total;
+                    scr_total += (uint64_t)grid * groups16[g].stride;
+                }
+            }
+            ctx->stats.items += (uint32_t)n16;
+            CK(ctx->items16.ensure(all.size() * sizeof(Item16)));
+            if (scr_total) CK(ctx->scratch16.ensure(scr_total * sizeof(uint2)));
+            CK(cudaMemcpyAsync(ctx->items16.p, all.data(), all.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all.size() * sizeof(Item16);
+            CK(cudaEventRecord(ctx->ev_s[0], s0));
+            for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_s[0], 0));
+            const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
+            int li = 0;
+            for (int g : gorder) {
+                const bool multi = g > kKMax;
+                const int K = multi ? g - (kKMax + 1) : g;
+                KArgs16 a;
+                memset(&a, 0, sizeof(a));
+                a.Q = Q.dev(); a.T = T.dev();
+                a.subst = ctx->d_subst.as<int16_t>();
+                a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+                a.items = ctx->items16.as<Item16>() + goff[g];
+                a.n_items = (uint32_t)groups16[g].items.size();
+                a.item_counter = ctx->counters.as<uint32_t>() + groups.size() + g;
+                a.scores = d_scores;
+                a.scratch = ctx->scratch16.as<uint2>() + groups16[g].scr_off;
+                a.scratch_stride = (uint32_t)groups16[g].stride;
+                Kernel16Fn fn = multi ? g_score16_multi[K] : g_score16_single[K];
+                const size_t smem = smem_for(K, C);
+                uint32_t grid = 0;
+                rc = grid_for(ctx, (KernelFn)fn, K, C, a.n_items, &grid);
+                if (rc) return rc;
+                cudaStream_t st = prof_groups ? s0 : ctx->streams[li % kStreams];
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (prof_groups) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+                fn<<<grid, kThreads, smem, st>>>(a);
+                CK(cudaGetLastError());
+                ctx->stats.launches++;
+                if (prof_groups) {
+                    cudaEventRecord(e1, st);
+                    cudaEventSynchronize(e1);
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    fprintf(stderr, "[bsa group16] K=%2d multi=%d items=%7zu cells=%.4e ms=%9.3f GCUPS=%8.1f\n", K, multi ? 1 : 0,
+                            groups16[g].items.size(), groups16[g].cells, ms, ms > 0 ? groups16[g].cells / 1e6 / ms : 0.0);
+                    cudaEventDestroy(e0); cudaEventDestroy(e1);
+                }
+                ++li;
+            }
+            for (int i = 1; i < kStreams; ++i) {
+                CK(cudaEventRecord(ctx->ev_s[i], ctx->streams[i]));
+                CK(cudaStreamWaitEvent(s0, ctx->ev_s[i], 0));
+            }
+        }
     }
     // pairs whose score range does not fit the packed lanes: direction-store path
     if (!fallback.empty()) {

@@ -538,6 +538,255 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Score-only, 16-bit packed lanes (one-vs-many, BASELINE configs[3]).  Two TEMPLATES of the
+// same column count share a warp: the low and high halves of every 32-bit register carry the
+// DP values of template A and template B, both fed by the same query stream, so one
+// VIADDMNMX.S16x2 / VIMNMX.S16x2 / VIADD.16x2 advances two cells.  No tie priorities are needed
+// for the score alone (SURVEY.md 8a note 5): the cell is 5 instructions per TWO cells
+//     t  = max(hdiag + T, e)      VIADDMNMX.S16x2
+//     h  = max(t, f)              VIMNMX.S16x2
+//     hg = h + GO                 VIADD.16x2
+//     e  = max(e + GE, hg)        VIADDMNMX.S16x2
+//     f  = max(f + GE, hg)        VIADDMNMX.S16x2
+// The host only routes template pairs here whose scores provably stay inside 16 bits.
+struct Item16 {
+    uint32_t tA, tB;        // tB == 0xffffffff: single template (high half idle)
+    uint32_t q_begin, q_end;
+    uint64_t outA, outB;    // result index of (q_begin, tA) / (q_begin, tB)
+};
+
+__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+template <int K, bool MULTI>
+__device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes, uint64_t g0, uint64_t g1,
+                                               const uint4* prof, const uint4* rsH, const uint4* rsF,
+                                               const int lane, const bool first, const bool lastp,
+                                               const int lastA, const int slotA, const int lastB,
+                                               const int slotB, const uint32_t hdiag0, const uint32_t GE,
+                                               const uint32_t GO, uint2* scratch, int32_t* __restrict__ scores,
+                                               uint64_t outA, uint64_t outB) {
+    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int U = MULTI ? 2 : 4;
+    const uint32_t X = (uint32_t)(g1 - g0);
+    const int span = (MULTI && !lastp) ? 31 : (lastA > lastB ? lastA : lastB);
+    const uint32_t nsteps = (X + (uint32_t)span + (U - 1)) / U * U;
+
+    int Ha[K], Hb[K], Fr[K], T[K];
+    load_vec<K>(Ha, rsH + lane);
+    load_vec<K>(Fr, rsF + lane);
+    uint32_t hdiag = hdiag0;
+    uint32_t hb = GO;                 // H[1][0] = gap_open, both halves
+    uint32_t oh = 0, oe = 0, emitted = 0;
+    const bool border = !MULTI || first;
+    const bool lane0 = lane == 0;
+    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
+    const uint8_t* p = codes + g0 - lane;
+    uint32_t b[U], nb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
+    uint2 sc_next = make_uint2(0u, 0u);
+    if (MULTI && !first && lane0 && X > 0) sc_next = scratch[0];
+
+#define BSA_STEP16_CORE(HO, HN, B, S)                                                             \
+        load_vec<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB));       \
+        uint32_t hin = __shfl_up_sync(0xffffffffu, oh, 1);                                        \
+        uint32_t e = __shfl_up_sync(0xffffffffu, oe, 1);                                          \
+        if (lane0) {                                                                              \
+            if (border) { hin = hb; e = add2(hb, GO); }                                           \
+            else { hin = sc_next.x; e = sc_next.y; }                                              \
+        }                                                                                         \
+        if (MULTI && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];                  \
+        hb = add2(hb, GE);                                                                        \
+        uint32_t hd = hdiag;                                                                      \
+        hdiag = hin;                                                                              \
+        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                           \
+            const uint32_t t = __viaddmax_s16x2(hd, (uint32_t)T[c], e);                           \
+            const uint32_t h = __vmaxs2(t, (uint32_t)Fr[c]);                                      \
+            const uint32_t hg = add2(h, GO);                                                      \
+            e = __viaddmax_s16x2(e, GE, hg);                                                      \
+            Fr[c] = (int)__viaddmax_s16x2((uint32_t)Fr[c], GE, hg);                               \
+            hd = (uint32_t)HO[c];                                                                 \
+            HN[c] = (int)h;                                                                       \
+        }                                                                                         \
+        oh = (uint32_t)HN[K - 1];                                                                 \
+        oe = e;                                                                                   \
+        if (MULTI && !lastp && lane == 31) {                                                      \
+            const uint32_t pos = (S)-31u;                                                         \
+            if (pos < X) scratch[pos] = make_uint2(oh, oe);                                       \
+        }
+#define BSA_STEP16_FAST(HO, HN, B, S) { BSA_STEP16_CORE(HO, HN, B, S) }
+#define BSA_STEP16(HO, HN, B, S)                                                                  \
+    {                                                                                             \
+        BSA_STEP16_CORE(HO, HN, B, S)                                                             \
+        if ((B)&kLastFlag) {                                                                      \
+            const uint32_t pos = (S) - (uint32_t)lane;                                            \
+            const bool valid = pos < X;                                                           \
+            if (lastp && valid && scores) {                                                       \
+                if (lane == lastA) {                                                              \
+                    int v = 0;                                                                    \
+                    _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slotA) v = HN[c];      \
+                    scores[outA + emitted] = (int)(short)(v & 0xffff);                            \
+                }                                                                                 \
+                if (lane == lastB) {                                                              \
+                    int v = 0;                                                                    \
+                    _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slotB) v = HN[c];      \
+                    scores[outB + emitted] = v >> 16;                                             \
+                }                                                                                 \
+            }                                                                                     \
+            emitted += valid ? 1u : 0u;                                                           \
+            load_vec<K>(HN, rsH + lane);                                                          \
+            load_vec<K>(Fr, rsF + lane);                                                          \
+            hdiag = hdiag0;                                                                       \
+            hb = GO;                                                                              \
+        }                                                                                         \
+    }
+
+    for (uint32_t s = 0; s < nsteps; s += U) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            nb[u] = ld_code(p + U + u);
+            any |= b[u];
+        }
+        p += U;
+        if (!__any_sync(0xffffffffu, any & kLastFlag)) {
+#pragma unroll
+            for (int u = 0; u < U; u += 2) {
+                BSA_STEP16_FAST(Ha, Hb, b[u], s + u)
+                BSA_STEP16_FAST(Hb, Ha, b[u + 1], s + u + 1)
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u += 2) {
+                BSA_STEP16(Ha, Hb, b[u], s + u)
+                BSA_STEP16(Hb, Ha, b[u + 1], s + u + 1)
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) b[u] = nb[u];
+    }
+#undef BSA_STEP16
+#undef BSA_STEP16_FAST
+#undef BSA_STEP16_CORE
+}
+
+struct KArgs16 {
+    SeqStoreDev Q, T;
+    const int16_t* subst;
+    int C, go, ge;
+    const Item16* items;
+    uint32_t n_items;
+    uint32_t* item_counter;
+    int32_t* scores;
+    uint2* scratch;
+    uint32_t scratch_stride;
+};
+
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_kernel(const KArgs16 a) {
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_chunk;
+    constexpr int ROW = KTraits<K>::ROW;
+    uint4* prof = smem;
+    uint4* rsH = smem + (size_t)a.C * ROW;
+    uint4* rsF = rsH + ROW;
+    const int lane = threadIdx.x & 31;
+    const uint32_t GE = pack2(a.ge), GO = pack2(a.go);
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t ii = s_item;
+        if (ii >= a.n_items) break;
+        const Item16 it = a.items[ii];
+        const bool hasB = it.tB != 0xffffffffu;
+        const uint64_t a0 = a.T.off[it.tA];
+        const uint32_t mA = (uint32_t)(a.T.off[it.tA + 1] - a0);
+        const uint64_t b0 = hasB ? a.T.off[it.tB] : 0;
+        const uint32_t mB = hasB ? (uint32_t)(a.T.off[it.tB + 1] - b0) : 0u;
+        const uint8_t* tcA = a.T.codes + a0;
+        const uint8_t* tcB = a.T.codes + b0;
+        const uint32_t mmax = mA > mB ? mA : mB;
+
+        const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
+        const uint64_t span = x1 - x0;
+        const uint64_t head = span - span * 3 / 16;
+        const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
+        uint32_t nsmall = (uint32_t)((span - head + kChunkSmall - 1) / kChunkSmall);
+        if (nsmall < (uint32_t)kWarpsPerCta) nsmall = kWarpsPerCta;
+        const uint32_t nch = nbig + nsmall;
+        const uint32_t npass = MULTI ? (mmax + 32 * K - 1) / (32 * K) : 1u;
+        uint2* scratch = MULTI ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : nullptr;
+
+        for (uint32_t pass = 0; pass < npass; ++pass) {
+            const uint32_t colbase = pass * 32 * K;
+            __syncthreads();
+            if (threadIdx.x == 0) s_chunk = 0;
+            // packed profile: low half template A, high half template B
+            for (int idx = threadIdx.x; idx < a.C * ROW; idx += blockDim.x) {
+                const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * v + e;
+                    const uint32_t col = colbase + ln * K + c;
+                    const int sa = (c < K && col < mA) ? (int)a.subst[code * a.C + (tcA[col] & kCodeMask)] : 0;
+                    const int sb = (c < K && col < mB) ? (int)a.subst[code * a.C + (tcB[col] & kCodeMask)] : 0;
+                    o[e] = ((uint32_t)sa & 0xffffu) | ((uint32_t)sb << 16);
+                }
+                prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            for (int r = threadIdx.x; r < ROW; r += blockDim.x) {
+                const int v = r >> 5, ln = r & 31;
+                uint32_t h[4], f[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const long long j = (long long)colbase + ln * K + 4 * v + e + 1;
+                    const int hv = (int)(a.go + (j - 1) * a.ge);
+                    h[e] = pack2(hv);
+                    f[e] = pack2(hv + a.go);
+                }
+                rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
+                rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
+            }
+            __syncthreads();
+            const bool lastp = (pass + 1 == npass);
+            // a template that ends in an earlier block never emits from this kernel: the host only
+            // pairs templates with the same number of blocks
+            const int lastA = (int)((mA - 1 - colbase) / K), slotA = (int)((mA - 1 - colbase) % K);
+            const int lastB = hasB ? (int)((mB - 1 - colbase) / K) : -1;
+            const int slotB = hasB ? (int)((mB - 1 - colbase) % K) : 0;
+            const long long jl = (long long)colbase + (long long)lane * K;
+            const uint32_t hdiag0 = jl == 0 ? 0u : pack2((int)(a.go + (jl - 1) * a.ge));
+            for (;;) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&s_chunk, 1u);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= nch) break;
+                const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
+                const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig
+                                                  : head + (span - head) * (c + 1 - nbig) / nsmall;
+                const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
+                const uint32_t qb = c + 1 == nch ? it.q_end
+                                                 : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
+                const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+                if (g1 > g0)
+                    stream_block16<K, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
+                                             lastp ? lastA : 31, slotA, lastp ? lastB : 31, slotB, hdiag0, GE, GO,
+                                             MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
+                                             it.outA + (qa - it.q_begin), it.outB + (qa - it.q_begin));
+            }
+        }
+    }
+}
+
 // K3 -- intra-task wavefront for long pairs.  Every WARP is an independent worker with its own
 // profile slice in shared memory; work items are (pair, column block) claimed in dependency
 // order from a global counter, so the block to the left of a claimed item is always already

@@ -237,3 +237,54 @@ def test_unsupported_gap_settings_are_refused(ctx):
     ctx.set_scoring("BLOSUM62", -10, -1)
     with pytest.raises(bs.BsaError):
         ctx.load_sequences(0, np.array([65, 255, 66], np.uint8), np.array([0, 3], np.uint64))
+
+
+def test_score_only_16bit_lanes(ctx, oracle_matrices):
+    """Score-only requests pair two templates per warp in s16x2 lanes (gotoh_score16_kernel);
+    scores must equal the oracle's (and the 32-bit kernel's)."""
+    rng = random.Random(41)
+    Q = [bytes(rng.choice(AA) for _ in range(rng.randint(1, 400))) for _ in range(90)]
+    T = [bytes(rng.choice(AA) for _ in range(n)) for n in
+         [1, 2, 31, 32, 33, 64, 100, 101, 233, 240, 250, 256, 300, 600, 640, 641, 700, 1290, 1300, 2000, 2100]]
+    T += [Q[3], Q[10][:50], Q[20] + Q[21]]
+    M = oracle_matrices["BLOSUM62"]
+    qr, qo = bs.pack(Q)
+    tr, to = bs.pack(T)
+    for go, ge in ((-10, -1), (-11, -2), (-4, -4)):
+        ctx.set_scoring("BLOSUM62", go, ge)
+        ctx.load_sequences(0, qr, qo)
+        ctx.load_sequences(1, tr, to)
+        s16, _ = ctx.one_vs_many(0, 1, want_identical=False)
+        ref = c_oracle.align_all_pairs(c_oracle.SeqSet(Q), c_oracle.SeqSet(T), M[0], M[1], go, ge, False,
+                                       n_threads=8, with_backtrace=False)
+        assert np.array_equal(s16, ref["score"]), (go, ge)
+        s32, _ = ctx.one_vs_many(0, 1, want_identical=True)
+        assert np.array_equal(s16, s32)
+    # the triangle (different query counts per template) and a set with an empty query
+    ctx.set_scoring("BLOSUM62", -10, -1)
+    ctx.load_sequences(0, qr, qo)
+    s_tri, _ = ctx.all_vs_all(0, want_identical=False)
+    ref = c_oracle.align_all_pairs(c_oracle.SeqSet(Q), c_oracle.SeqSet(Q), M[0], M[1], -10, -1, True, n_threads=8,
+                                   with_backtrace=False)
+    assert np.array_equal(s_tri, ref["score"])
+    Q2 = Q[:10] + [b""] + Q[10:20]
+    q2r, q2o = bs.pack(Q2)
+    ctx.load_sequences(0, q2r, q2o)
+    s_e, _ = ctx.one_vs_many(0, 1, want_identical=False)
+    ref = c_oracle.align_all_pairs(c_oracle.SeqSet(Q2), c_oracle.SeqSet(T), M[0], M[1], -10, -1, False, n_threads=8,
+                                   with_backtrace=False)
+    assert np.array_equal(s_e, ref["score"])
+
+
+def test_score_only_long_sequences_leave_16bit_lanes(ctx, oracle_matrices):
+    """min(len) * 11 > 32k cannot be held in 16 bits: those templates take the 32-bit kernel."""
+    res, off = synth.generate(6, seed=8, dist=0, lo=2500, hi=3900)
+    ctx.set_scoring("BLOSUM62", -10, -1)
+    ctx.load_sequences(0, res, off)
+    ctx.load_sequences(1, res, off)
+    s, _ = ctx.one_vs_many(0, 1, want_identical=False)
+    S = c_oracle.SeqSet.from_packed(res, off)
+    M = oracle_matrices["BLOSUM62"]
+    ref = c_oracle.align_all_pairs(S, S, M[0], M[1], -10, -1, False, n_threads=8, with_backtrace=False)
+    assert np.array_equal(s, ref["score"])
+    assert ctx.stats()["items"] > 0
