@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the number of sequences (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="allvsall", choices=["allvsall", "onevsmany"],
+                    help="allvsall = BASELINE configs[1] (the headline, default); onevsmany = configs[3] shape "
+                         "(1,000 queries x 125,000 database sequences per GPU, score only, 16-bit lanes)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,15 +189,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    res, off, name = workload(world, args.n)
-    n = len(off) - 1
-    counts = np.arange(n, dtype=np.uint32)
+    ovm = args.workload == "onevsmany"
     ctx = Context(local_rank)
     ctx.set_scoring(SubstitutionMatrix.load(MATRIX), GO, GE)
-    ctx.load_sequences(0, res, off)
-    bounds = ctx.plan_shards(0, 0, counts, world)          # identical on every rank: no exchange
-    t0, t1 = int(bounds[rank]), int(bounds[rank + 1])
-    n_res = int(counts[t0:t1].astype(np.int64).sum())
+    if ovm:
+        from bioshell_b200 import synth
+        qres, qoff = synth.config("cfg4q")
+        res, off = synth.config("cfg4db", n=args.n or 125000 * world)
+        n = len(off) - 1
+        name = "cfg4 shape: %d queries x %d database sequences (UniRef50-like lengths), score only, " \
+               "BLOSUM62 gap -10/-1" % (len(qoff) - 1, n)
+        counts = None
+        ctx.load_sequences(1, qres, qoff)
+        ctx.load_sequences(0, res, off)
+        q_set, ops_per_cell, peak_which, want_i = 1, 2.5, 6, False
+        bounds = ctx.plan_shards(1, 0, None, world)
+        t0, t1 = int(bounds[rank]), int(bounds[rank + 1])
+        n_res = (t1 - t0) * (len(qoff) - 1)
+    else:
+        res, off, name = workload(world, args.n)
+        n = len(off) - 1
+        counts = np.arange(n, dtype=np.uint32)
+        ctx.load_sequences(0, res, off)
+        q_set, ops_per_cell, peak_which, want_i = 0, OPS_PER_CELL, 0, True
+        bounds = ctx.plan_shards(0, 0, counts, world)          # identical on every rank: no exchange
+        t0, t1 = int(bounds[rank]), int(bounds[rank + 1])
+        n_res = int(counts[t0:t1].astype(np.int64).sum())
 
     # outputs in HBM for the device-timed leg, pinned host buffers for the e2e leg
     d_scores = torch.empty(max(n_res, 1), dtype=torch.int32, device="cuda")
@@ -205,13 +225,16 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def step_device():
-        ctx.align_all_pairs(0, 0, counts, t0, t1, scores=d_scores.data_ptr(), n_identical=d_nid.data_ptr(),
-                            device_out=True)
+        ctx.align_all_pairs(q_set, 0, counts, t0, t1, scores=d_scores.data_ptr(), want_identical=want_i,
+                            n_identical=d_nid.data_ptr() if want_i else None, device_out=True)
         return ctx.stats()
 
     def step_e2e():
         ctx.load_sequences(0, h_res.numpy(), off)
-        ctx.align_all_pairs(0, 0, counts, t0, t1, scores=h_scores.numpy(), n_identical=h_nid.numpy())
+        if ovm:
+            ctx.load_sequences(1, qres, qoff)
+        ctx.align_all_pairs(q_set, 0, counts, t0, t1, scores=h_scores.numpy(), want_identical=want_i,
+                            n_identical=h_nid.numpy() if want_i else None)
         return ctx.stats()
 
     for _ in range(max(args.warmup, 3)):
@@ -244,7 +267,7 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - e0) * 1e3
 
-    peak_ops, peak_mhz = ctx.measure_int_peak(0)
+    peak_ops, peak_mhz = ctx.measure_int_peak(peak_which)
 
     # whole-job aggregates: max time over ranks, sum of units over ranks
     tv = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -260,12 +283,12 @@ def main():
         gcups = cells / 1e9 / (ms_per_step / 1e3)
         e2e_gcups = cells / 1e9 / (e2e_ms / args.steps / 1e3)
         per_gpu_cells_s = gcups * 1e9 / world
-        achieved = per_gpu_cells_s * OPS_PER_CELL
+        achieved = per_gpu_cells_s * ops_per_cell
         line = {
-            "metric": "all-vs-all global alignment throughput", "value": gcups, "unit": "GCUPS",
+            "metric": ("one-vs-many" if ovm else "all-vs-all") + " global alignment throughput", "value": gcups, "unit": "GCUPS",
             "pairs_per_s": pairs / (ms_per_step / 1e3), "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16x2" if ovm else "int32", "data": "synthetic",
             "config": {"workload": name, "n_sequences": n, "pairs": int(pairs), "cells": int(cells),
                        "parallelism": "template-range shards x%d, no collective" % world,
                        "l2": "256 MiB buffer rewritten between timed steps (inputs are 2.9 MB; outputs 8 B/pair stream to HBM)",
@@ -284,12 +307,12 @@ def main():
                          # capture in profiles/r1_ncu_summary_final.md; algorithmic HBM bytes of that
                          # launch are ~8 B/pair of results + the 2.9 MB sequence store
                          "traffic": 3903744,
-                         "note": "integer/DPX issue roofline per GPU: cells/s x %d lane-instructions per cell vs the same "
+                         "note": "integer/DPX issue roofline per GPU: cells/s x %.1f lane-instructions per cell vs the same "
                                  "instruction mix measured live by bsa_measure_int_peak (of measured; SM clock %.0f MHz "
-                                 "during that probe). HBM is not the bound: algorithmic traffic is 8 B/pair." % (OPS_PER_CELL, peak_mhz),
+                                 "during that probe). HBM is not the bound: algorithmic traffic is 8 B/pair." % (ops_per_cell, peak_mhz),
                          "hbm_algorithmic_gbs": (pairs * 8 / world) / (ms_per_step / 1e3) / 1e9},
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not ovm:
             threads = os.cpu_count() or 1
             g0, _, dt0 = cpu_reference_run(res, off, 32 * threads, threads, 0)
             cnt = int(max(32 * threads, min(100000, 32 * threads * 12.0 / max(dt0, 1e-3))))

@@ -132,7 +132,6 @@ template <int K>
 __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rsF,
                                               const uint8_t* __restrict__ tc, uint32_t m,
                                               uint32_t colbase, const KArgs& a, const Consts& cs) {
-    constexpr int V = KTraits<K>::V;
     constexpr int ROW = KTraits<K>::ROW;
     const int C = a.C;
     const int S = 1 << (cs.cs + 2);
