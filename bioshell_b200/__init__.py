@@ -2,7 +2,7 @@
 BioShell's aligner API.  See DESIGN.md; the C ABI is include/bioshell_align.h."""
 from ._lib import BsaError, LIB_PATH  # noqa: F401
 from .alignment import (AlignmentReporter, AlignmentStatistics, CollectReporter, Context,  # noqa: F401
-                        GlobalAligner, MultiReporter, PairResults, SequenceIdentityMatrix,
+                        GlobalAligner, LocalAlignment, MultiReporter, PairResults, SequenceIdentityMatrix,
                         align_all_pairs, align_all_vs_all, align_one_vs_many, align_pairs_batched,
                         aligned_sequences, aligned_strings, aligned_symbols, triangle_counts)
 from .scoring import SubstitutionMatrix, SubstitutionMatrixList, ncbi_text  # noqa: F401

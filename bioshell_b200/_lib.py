@@ -20,7 +20,7 @@ SYMBOLS = ["bsa_device_count", "bsa_create", "bsa_destroy", "bsa_last_error",
            "bsa_parse_ncbi_matrix", "bsa_set_scoring", "bsa_load_sequences", "bsa_align_all_pairs",
            "bsa_all_vs_all", "bsa_one_vs_many", "bsa_plan_shards", "bsa_align_pairs_paths",
            "bsa_host_alloc_pinned", "bsa_host_free_pinned", "bsa_get_stats", "bsa_measure_int_peak",
-           "bsa_hclust"]
+           "bsa_hclust", "bsa_local_align_pairs"]
 
 
 class BsaError(RuntimeError):
@@ -68,6 +68,7 @@ def lib():
     L.bsa_plan_shards.argtypes = [vp, C.c_int, C.c_int, vp, u32, vp]
     L.bsa_align_pairs_paths.argtypes = [vp, C.c_int, C.c_int, vp, vp, u64, vp, vp, vp, vp]
     L.bsa_hclust.argtypes = [vp, u32, vp, C.c_int, u32, vp, vp, vp]
+    L.bsa_local_align_pairs.argtypes = [vp, C.c_int, C.c_int, vp, vp, u64] + [vp] * 7
     L.bsa_host_alloc_pinned.argtypes = [C.c_size_t]
     L.bsa_host_alloc_pinned.restype = vp
     L.bsa_host_free_pinned.argtypes = [vp]

@@ -136,6 +136,25 @@ class Context:
             paths = [raw[int(poff[i]):int(poff[i + 1])] for i in range(n)]
         return scores, nid, paths
 
+    def local_align_pairs(self, q_set, t_set, q_idx, t_idx, want_paths=True):
+        """bsa_local_align_pairs -> dict(score, end_q, end_t, start_q, start_t, paths)."""
+        qi = np.ascontiguousarray(q_idx, np.uint32)
+        ti = np.ascontiguousarray(t_idx, np.uint32)
+        n = len(qi)
+        lq = self._sets[int(q_set)][1][qi.astype(np.int64)] if n else np.zeros(0, np.int64)
+        lt = self._sets[int(t_set)][1][ti.astype(np.int64)] if n else np.zeros(0, np.int64)
+        out = {k: np.zeros(n, np.uint32) for k in ("end_q", "end_t", "start_q", "start_t")}
+        out["score"] = np.zeros(n, np.int32)
+        poff = np.zeros(n + 1, np.uint64)
+        buf = np.zeros(int((lq + lt).sum()) + 1, np.uint8) if want_paths else None
+        self._ck(self._L.bsa_local_align_pairs(self._h, int(q_set), int(t_set), _p(qi), _p(ti), n, _p(out["score"]),
+                                               _p(out["end_q"]), _p(out["end_t"]), _p(out["start_q"]),
+                                               _p(out["start_t"]), _p(buf), _p(poff)))
+        if want_paths:
+            raw = buf.tobytes()
+            out["paths"] = [raw[int(poff[i]):int(poff[i + 1])] for i in range(n)]
+        return out
+
     def plan_shards(self, q_set, t_set, q_counts, n_shards):
         qc = None if q_counts is None else np.ascontiguousarray(q_counts, np.uint32)
         b = np.zeros(n_shards + 1, np.uint32)
@@ -392,6 +411,36 @@ def align_all_pairs(queries, templates, matrix, gap_open, gap_extend, if_triangl
             aq, at = aligned_sequences(path, queries[int(q)], templates[int(t)], "-")
             reporter.report(aq, at)
     return len(t_all)
+
+
+class LocalAlignment:
+    """Single-pair convenience with the reference's method names (local.rs:18-284)."""
+
+    def __init__(self, max_seq_length, ctx=None):
+        self.max_length = max_seq_length + 1
+        self._ctx = ctx or default_context()
+        self._r = None
+
+    def align(self, query, template, matrix, gap_open, gap_extend):
+        q = query.encode() if isinstance(query, str) else bytes(query)
+        t = template.encode() if isinstance(template, str) else bytes(template)
+        if len(q) >= self.max_length or len(t) >= self.max_length:
+            raise IndexError("index out of bounds: sequence longer than the aligner capacity")
+        self._ctx.set_scoring(matrix, gap_open, gap_extend)
+        res, off = pack([q, t])
+        self._ctx.load_sequences(7, res, off)
+        self._r = self._ctx.local_align_pairs(7, 7, [0], [1])
+        return int(self._r["score"][0])
+
+    def backtrace(self):
+        """-> (path, query_start, template_start)  (local.rs:213-273)"""
+        return self._r["paths"][0].decode(), int(self._r["start_q"][0]), int(self._r["start_t"][0])
+
+    def recent_score(self):
+        return int(self._r["score"][0])
+
+    def recent_end_point(self):
+        return int(self._r["end_q"][0]), int(self._r["end_t"][0])
 
 
 class GlobalAligner:

@@ -132,6 +132,8 @@ inline int bitlen(uint64_t x) {
 typedef void (*KernelFn)(const KArgs);
 KernelFn g_stream_single[kKMax + 1], g_stream_multi[kKMax + 1], g_dirs[kKMax + 1];
 typedef void (*Kernel16Fn)(const KArgs16);
+typedef void (*KernelLocalFn)(const KArgs, LocalOut*);
+KernelLocalFn g_local[kKMax + 1];
 Kernel16Fn g_score16_single[kKMax + 1], g_score16_multi[kKMax + 1];
 
 template <int K>
@@ -160,6 +162,13 @@ void register_kernels() {
     g_dirs[16] = gotoh_dirs_kernel<16>;
     g_dirs[24] = gotoh_dirs_kernel<24>;
     g_dirs[32] = gotoh_dirs_kernel<32>;
+    g_local[2] = gotoh_local_kernel<2>;
+    g_local[4] = gotoh_local_kernel<4>;
+    g_local[8] = gotoh_local_kernel<8>;
+    g_local[12] = gotoh_local_kernel<12>;
+    g_local[16] = gotoh_local_kernel<16>;
+    g_local[24] = gotoh_local_kernel<24>;
+    g_local[32] = gotoh_local_kernel<32>;
     done = true;
 }
 size_t smem_for(int K, int C) { return (size_t)(C + 2) * ((K + 3) / 4) * 32 * sizeof(uint4); }
@@ -251,7 +260,8 @@ struct PairReq { uint32_t q, t; uint64_t out; };
 int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<PairReq>& reqs,
                    int32_t* d_scores, uint32_t* d_nid, uint8_t* path_buf,
                    const std::vector<uint64_t>* slot_off, std::vector<uint32_t>* path_len,
-                   const std::vector<uint64_t>* req_index) {
+                   const std::vector<uint64_t>* req_index, LocalOut* d_lout = nullptr) {
+    const bool local = d_lout != nullptr;   // LocalAlignment instead of GlobalAligner
     if (reqs.empty()) return BSA_OK;
     const int C = std::max(ctx->ncodes, 1);
     // order by template so a CTA shares one profile between its warps
@@ -275,7 +285,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         while (pos < order.size()) {
             const PairReq& r = reqs[order[pos]];
             const uint64_t n = Q.len(r.q), m = T.len(r.t);
-            const bool wave = m >= 4096 && wave_warps >= 1;   // >= 16 column blocks of 256
+            const bool wave = !local && m >= 4096 && wave_warps >= 1;   // >= 16 column blocks of 256
             const int K = wave ? kWaveK : choose_dirs_k(m, C);
             if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
             const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
@@ -360,7 +370,18 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             a.scratch = ctx->scratch.as<uint2>(); a.scratch_stride = 0;
             a.pairs = ctx->pairs.as<PairRec>();
             a.dirs = ctx->dirs.as<uint32_t>();
-            int rc = launch(ctx, g_dirs[K], K, a, st);
+            int rc = BSA_OK;
+            if (local) {
+                const size_t smem = smem_for(K, a.C);
+                uint32_t grid = 0;
+                rc = grid_for(ctx, (KernelFn)g_local[K], K, a.C, a.n_items, &grid);
+                if (rc) return rc;
+                g_local[K]<<<grid, kThreads, smem, st>>>(a, d_lout);
+                CK(cudaGetLastError());
+                ctx->stats.launches++;
+            } else {
+                rc = launch(ctx, g_dirs[K], K, a, st);
+            }
             if (rc) return rc;
             gi = gj;
             ++group;
@@ -404,7 +425,8 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         ta.path_start = ctx->pstart.as<uint32_t>();
         ta.nident = d_nid;
         ta.status = ctx->status.as<uint32_t>();
-        traceback_kernel<<<(ta.n_pairs + 63) / 64, 64, 0, st>>>(ta);
+        if (local) traceback_local_kernel<<<(ta.n_pairs + 63) / 64, 64, 0, st>>>(ta, d_lout);
+        else traceback_kernel<<<(ta.n_pairs + 63) / 64, 64, 0, st>>>(ta);
         CK(cudaGetLastError());
         ctx->stats.launches++;
         uint32_t status = 0;
@@ -1146,6 +1168,76 @@ int bsa_align_pairs_paths(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
             } else {
                 memmove(path_buf + w, path_buf + slot_off[p] + (slot - plen[p]), plen[p]);
             }
+            w += plen[p];
+            path_off[p + 1] = w;
+        }
+    } else if (path_off) {
+        for (uint64_t p = 0; p < n_pairs; ++p) path_off[p + 1] = 0;
+    }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));
+    ctx->stats.kernel_ms = ms;
+    ctx->stats.total_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return BSA_OK;
+}
+
+// LocalAlignment::align + backtrace + recent_end_point (bioshell-seq/src/alignment/local.rs:83-284)
+int bsa_local_align_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_idx, const uint32_t* t_idx,
+                          uint64_t n_pairs, int32_t* scores, uint32_t* end_q, uint32_t* end_t, uint32_t* start_q,
+                          uint32_t* start_t, uint8_t* path_buf, uint64_t* path_off) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    const auto wall0 = std::chrono::steady_clock::now();
+    if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets)
+        return fail(ctx, BSA_ERR_BAD_ARG, "bad set id");
+    const SeqSet &Q = ctx->sets[q_set], &T = ctx->sets[t_set];
+    if (!Q.loaded || !T.loaded) return fail(ctx, BSA_ERR_EMPTY, "sequence set not loaded");
+    if (n_pairs && (!q_idx || !t_idx)) return fail(ctx, BSA_ERR_BAD_ARG, "null pair list");
+    if (path_buf && !path_off) return fail(ctx, BSA_ERR_BAD_ARG, "path_buf needs path_off");
+    CK(cudaSetDevice(ctx->device));
+    int rc = sync_scoring(ctx);
+    if (rc) return rc;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.pairs = n_pairs;
+    if (path_off) path_off[0] = 0;
+    if (n_pairs == 0) return BSA_OK;
+    std::vector<PairReq> reqs;
+    std::vector<uint64_t> req_index;
+    std::vector<uint64_t> slot_off(n_pairs + 1, 0);
+    std::vector<uint32_t> plen(n_pairs, 0);
+    double cells = 0;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        if (q_idx[p] >= Q.n || t_idx[p] >= T.n) return fail(ctx, BSA_ERR_BAD_ARG, "pair index out of range");
+        const uint64_t n = Q.len(q_idx[p]), m = T.len(t_idx[p]);
+        slot_off[p + 1] = slot_off[p] + n + m;
+        cells += (double)n * (double)m;
+        if (n && m) { reqs.push_back(PairReq{q_idx[p], t_idx[p], p}); req_index.push_back(p); }
+    }
+    ctx->stats.cells = (uint64_t)cells;
+    DevBuf& lbuf = ctx->out_nid;   // reused as the LocalOut array of this call
+    CK(lbuf.ensure(n_pairs * sizeof(LocalOut)));
+    cudaStream_t s0 = ctx->streams[0];
+    CK(cudaMemsetAsync(lbuf.p, 0, n_pairs * sizeof(LocalOut), s0));   // empty sequences: score 0, (0,0)
+    CK(cudaEventRecord(ctx->ev_start, s0));
+    rc = run_pairs_dirs(ctx, Q, T, reqs, nullptr, nullptr, path_buf, &slot_off, &plen, &req_index, lbuf.as<LocalOut>());
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_end, s0));
+    std::vector<LocalOut> lo(n_pairs);
+    CK(cudaMemcpyAsync(lo.data(), lbuf.p, n_pairs * sizeof(LocalOut), cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    ctx->stats.d2h_bytes += n_pairs * sizeof(LocalOut);
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        if (scores) scores[p] = lo[p].score;
+        if (end_q) end_q[p] = lo[p].end_q;
+        if (end_t) end_t[p] = lo[p].end_t;
+        if (start_q) start_q[p] = lo[p].start_q;
+        if (start_t) start_t[p] = lo[p].start_t;
+    }
+    if (path_buf) {
+        uint64_t w = 0;
+        for (uint64_t p = 0; p < n_pairs; ++p) {
+            const uint64_t slot = slot_off[p + 1] - slot_off[p];
+            if (plen[p]) memmove(path_buf + w, path_buf + slot_off[p] + (slot - plen[p]), plen[p]);
             w += plen[p];
             path_off[p + 1] = w;
         }

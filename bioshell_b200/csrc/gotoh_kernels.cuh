@@ -111,6 +111,7 @@ struct Consts {
     int GE, GO, MASK, PH, PV, T_PAD;
     int hb0;  // packed H[1][0] = gap_open
     int cs;
+    bool local;   // Smith-Waterman borders: everything starts at 0
 };
 
 template <int K>
@@ -165,9 +166,9 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
         for (int e = 0; e < 4; ++e) {
             const int c = 4 * v + e;
             const long long j = (long long)colbase + lane * K + c + 1;  // DP column
-            const int hv = (int)((a.go + (j - 1) * a.ge) * S);
+            const int hv = cs.local ? 0 : (int)((a.go + (j - 1) * a.ge) * S);
             h[e] = hv;
-            f[e] = hv + cs.GO;
+            f[e] = cs.local ? 0 : hv + cs.GO;
         }
         rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
         rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -192,28 +193,37 @@ __device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict_
 // copies are needed).  `one` is the runtime constant 1: `x * one + y` keeps the two plain
 // additions of the cell on the FMA pipe (IMAD) instead of the ALU pipe, which the six
 // LOP3 / VIMNMX3 / VIADDMNMX instructions saturate.
-template <int K, bool DIRS>
+// LOCAL (Smith-Waterman, bioshell-seq/src/alignment/local.rs:120-203): the same recurrences
+// with the three maxima clamped at zero (the DPX *_relu forms).  A value whose score field is
+// <= 0 is the reference's STOP: it carries direction 0 and clears to exactly 0 under MASK.
+template <int K, bool DIRS, bool LOCAL = false>
 __device__ __forceinline__ void cell_row(const int (&Hold)[K], int (&Hnew)[K], int (&Fr)[K],
                                          const int (&T)[K], int hd, int& er, const Consts& cs,
-                                         const int one, uint32_t (&dw)[KTraits<K>::W]) {
+                                         const int one, uint32_t (&dw)[KTraits<K>::W], int& rowmax) {
 #pragma unroll
     for (int c = 0; c < K; ++c) {
         const int e = er | cs.PH;
         const int f = Fr[c] | cs.PV;
         const int d = hd * one + T[c];
-        const int h = max3_s32(d, e, f);
+        const int h = LOCAL ? __vimax3_s32_relu(d, e, f) : max3_s32(d, e, f);
         if (DIRS) {
-            const uint32_t nib = ((uint32_t)h & 3u) | ((((uint32_t)er | (uint32_t)Fr[c]) & 3u) << 2);
+            uint32_t hdir = (uint32_t)h & 3u;
+            if (LOCAL) hdir = h >= 4 ? hdir : 0u;      // score <= 0: STOP (arrows = 0, local.rs:158-181)
+            const uint32_t nib = hdir | ((((uint32_t)er | (uint32_t)Fr[c]) & 3u) << 2);
             dw[c >> 3] = (dw[c >> 3] << 4) | nib;
         }
         const int hc = h & cs.MASK;
         const int hg = hc * one + cs.GO;
-        er = addmax_s32(e, cs.GE, hg);
-        Fr[c] = addmax_s32(f, cs.GE, hg);
+        er = LOCAL ? __viaddmax_s32_relu(e, cs.GE, hg) : addmax_s32(e, cs.GE, hg);
+        Fr[c] = LOCAL ? __viaddmax_s32_relu(f, cs.GE, hg) : addmax_s32(f, cs.GE, hg);
+        if (LOCAL) rowmax = rowmax > hc ? rowmax : hc;
         hd = Hold[c];
         Hnew[c] = hc;
     }
 }
+
+// best cell of a local alignment as one lane sees it (first strict maximum in row-major order)
+struct LaneBest { int v; uint32_t row, col; };
 
 // Stream the residues codes[g0 .. g1) (whole sequences, back to back, last residue
 // of each flagged) through the 32 lanes for ONE column block of the template.
@@ -238,7 +248,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // intra-task wavefront).  The block to the left publishes how many boundary entries it has
 // written (`prog_out`, release store every 32 rows); this block waits on `prog_in` (acquire)
 // before it consumes them.  Without WAVE, scratch_out == scratch and the pointers are null.
-template <int K, bool DIRS, bool MULTI, bool WAVE = false>
+template <int K, bool DIRS, bool MULTI, bool WAVE = false, bool LOCAL = false>
 __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
                                              uint64_t g1, const uint4* prof, const uint4* rsH,
                                              const uint4* rsF, const int lane, const bool first,
@@ -250,7 +260,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                                              uint32_t* __restrict__ nident, uint64_t out_idx0,
                                              uint32_t* __restrict__ dirs, uint2* scratch_out = nullptr,
                                              const uint32_t* prog_in = nullptr,
-                                             uint32_t* prog_out = nullptr) {
+                                             uint32_t* prog_out = nullptr, LaneBest* lane_best = nullptr,
+                                             const uint32_t colbase = 0) {
     constexpr int W = KTraits<K>::W;
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
     if (!WAVE) scratch_out = scratch;
@@ -270,6 +281,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     const bool border = !MULTI || first;
     const bool lane0 = lane == 0;
     const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
+    LaneBest lbest{0, 0u, 0u};
 
     const uint8_t* p = codes + g0 - lane;   // lane's position at step 0 (may sit in the padding)
     uint32_t b[U], nb[U];
@@ -289,8 +301,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         int er = __shfl_up_sync(0xffffffffu, oe, 1);                                              \
         if (lane0) {                                                                              \
             if (border) { /* H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101) */ \
-                hin = hb;                                                                         \
-                er = hb + cs.GO;                                                                  \
+                hin = LOCAL ? 0 : hb;            /* local: H[i][0] = E[i][1] = 0 (local.rs:116) */ \
+                er = LOCAL ? 0 : hb + cs.GO;                                                      \
             } else {                                                                              \
                 hin = (int)sc_next.x;                                                             \
                 er = (int)sc_next.y;                                                              \
@@ -302,7 +314,16 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         hdiag = hin;                                                                              \
         uint32_t dw[W];                                                                           \
         _Pragma("unroll") for (int w = 0; w < W; ++w) dw[w] = 0u;                                 \
-        cell_row<K, DIRS>(HO, HN, Fr, T, hd, er, cs, one, dw);                                    \
+        int rowmax = 0;                                                                           \
+        cell_row<K, DIRS, LOCAL>(HO, HN, Fr, T, hd, er, cs, one, dw, rowmax);                     \
+        if (LOCAL && rowmax > lbest.v && (S) - (uint32_t)lane < X) {                              \
+            /* a new best in this lane: remember the row and the first column that holds it */   \
+            lbest.v = rowmax;                                                                     \
+            lbest.row = (S) - (uint32_t)lane;                                                     \
+            uint32_t cc = 0;                                                                      \
+            _Pragma("unroll") for (int c = K - 1; c >= 0; --c) if (HN[c] == rowmax) cc = (uint32_t)c; \
+            lbest.col = colbase + (uint32_t)lane * K + cc;                                        \
+        }                                                                                         \
         oh = HN[K - 1];                                                                           \
         oe = er;                                                                                  \
         if (DIRS) {                                                                               \
@@ -325,7 +346,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             /* lane back on the top border for the next query of the stream.               */     \
             const uint32_t pos = (S) - (uint32_t)lane;                                            \
             const bool valid = pos < X;                                                           \
-            if (lastp && valid && lane == lane_last) {                                            \
+            if (!LOCAL && lastp && valid && lane == lane_last) {                                  \
                 int v = 0;                                                                        \
                 _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = HN[c];      \
                 const uint64_t k = out_idx0 + emitted;                                            \
@@ -375,6 +396,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 #undef BSA_STEP
 #undef BSA_STEP_FAST
 #undef BSA_STEP_CORE
+    if (LOCAL) *lane_best = lbest;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
@@ -388,7 +410,7 @@ __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__
 }
 
 template <int K>
-__device__ __forceinline__ Consts make_consts(int go, int ge, int cshift) {
+__device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool local = false) {
     Consts cs;
     cs.cs = cshift;
     const int S = 1 << (cshift + 2);
@@ -397,8 +419,12 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift) {
     cs.MASK = ~(3 << cshift);
     cs.PH = 2 << cshift;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
     cs.PV = 1 << cshift;   // F: vertical, gap in the template
-    cs.T_PAD = 3 << cshift;
+    // padded columns: neutral in global mode; in local mode they must never score, so that no
+    // cell outside the template can reach the best score (anything they inherit through E/F is
+    // strictly below a real cell of the same row)
+    cs.T_PAD = local ? -(1 << 24) : 3 << cshift;
     cs.hb0 = go * S;
+    cs.local = local;
     return cs;
 }
 
@@ -933,6 +959,126 @@ __global__ void traceback_kernel(const TraceArgs a) {
     while (i > 0) { --pos; if (out) out[pos] = '|'; --i; }
     a.path_start[p] = pos;
     if (a.nident) a.nident[pr.out] = nid;
+}
+
+// Local alignment (LocalAlignment::align, bioshell-seq/src/alignment/local.rs:83-207): the
+// direction-store kernel with LOCAL recurrences.  Every lane tracks the first strict maximum of
+// H over its cells; the warp merges them by (score desc, row asc, column asc), which is the
+// reference's row-major first-strict-maximum (E and F can never exceed H in the same cell, so
+// best_state is always H, local.rs:185-202).
+struct LocalOut {
+    int32_t score;
+    uint32_t end_q, end_t;      // recent_end_point(): 1-based DP indices of the best cell
+    uint32_t start_q, start_t;  // backtrace(): where the walk stopped (0-based start offsets)
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) gotoh_local_kernel(const KArgs a, LocalOut* __restrict__ lout) {
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_item;
+    constexpr int ROW = KTraits<K>::ROW;
+    constexpr int W = KTraits<K>::W;
+    uint4* prof = smem;
+    uint4* rsH = smem + (size_t)a.C * ROW;
+    uint4* rsF = rsH + ROW;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t ii = s_item;
+        if (ii >= a.n_items) break;
+        const Item it = a.items[ii];
+        const uint64_t t0 = a.T.off[it.t];
+        const uint32_t m = (uint32_t)(a.T.off[it.t + 1] - t0);
+        const uint8_t* tc = a.T.codes + t0;
+        const Consts cs = make_consts<K>(a.go, a.ge, 0, true);
+        const uint32_t npass = (m + 32 * K - 1) / (32 * K);
+
+        for (uint32_t pass = 0; pass < npass; ++pass) {
+            const uint32_t colbase = pass * 32 * K;
+            __syncthreads();
+            build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
+            __syncthreads();
+            const bool lastp = (pass + 1 == npass);
+            for (uint32_t pi = it.q_begin + warp; pi < it.q_end; pi += kWarpsPerCta) {
+                const PairRec pr = a.pairs[pi];
+                const uint64_t g0 = a.Q.off[pr.q], g1 = a.Q.off[pr.q + 1];
+                const uint32_t n = (uint32_t)(g1 - g0);
+                uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 32) * 32 * W;
+                LaneBest lb;
+                stream_block<K, true, true, false, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
+                                                         31, 0, 0, cs, a.one, a.scratch + pr.scr_off, nullptr,
+                                                         nullptr, 0, dirs, nullptr, nullptr, nullptr, &lb, colbase);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    LaneBest o;
+                    o.v = __shfl_down_sync(0xffffffffu, lb.v, off);
+                    o.row = __shfl_down_sync(0xffffffffu, lb.row, off);
+                    o.col = __shfl_down_sync(0xffffffffu, lb.col, off);
+                    if (o.v > lb.v || (o.v == lb.v && (o.row < lb.row || (o.row == lb.row && o.col < lb.col)))) lb = o;
+                }
+                if (lane == 0) {
+                    LocalOut cur;
+                    if (pass == 0) cur = LocalOut{0, 0u, 0u, 0u, 0u};
+                    else cur = lout[pr.out];
+                    const int sc = lb.v >> 2;
+                    // earlier blocks hold smaller columns: a later block wins ties only on an earlier row
+                    if (sc > cur.score || (sc == cur.score && sc > 0 && lb.row + 1 < cur.end_q)) {
+                        cur.score = sc;
+                        cur.end_q = lb.row + 1;
+                        cur.end_t = lb.col + 1;
+                    }
+                    lout[pr.out] = cur;
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// LocalAlignment::backtrace (local.rs:213-273): from the best cell, state H, until a STOP
+__global__ void traceback_local_kernel(const TraceArgs a, LocalOut* __restrict__ lout) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_pairs) return;
+    const PairRec pr = a.pairs[p];
+    const uint32_t n = (uint32_t)(a.Q.off[pr.q + 1] - a.Q.off[pr.q]);
+    const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - a.T.off[pr.t]);
+    const uint32_t K = pr.k, W = (K + 7) / 8, BK = 32 * K;
+    const size_t plane = (size_t)(n + 32) * 32 * W;
+    const uint32_t* dirs = a.dirs + pr.dir_off;
+    uint8_t* out = a.path ? a.path + pr.path_off : nullptr;
+    LocalOut lo = lout[pr.out];
+    uint32_t pos = n + m, i = lo.end_q, j = lo.end_t;
+    int st = 0;
+    while (i > 0 && j > 0) {
+        const uint32_t col = j - 1, pass = col / BK, lc = col - pass * BK;
+        const uint32_t lane = lc / K, c = lc - lane * K;
+        const uint32_t step = (i - 1) + lane, w = c >> 3;
+        const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
+        const uint32_t sh = 4 * (cnt - 1 - (c & 7));
+        const uint32_t nib = (dirs[pass * plane + ((size_t)step * 32 + lane) * W + w] >> sh) & 15u;
+        if (st == 0) {
+            const uint32_t hd = nib & 3u;
+            if (hd == 0u) break;                                   // arrows == 0: STOP
+            if (hd == 3u) { --pos; if (out) out[pos] = '*'; --i; --j; }
+            else if (hd == 2u) st = 1;
+            else st = 2;
+        } else if (st == 1) {
+            --pos; if (out) out[pos] = '-';
+            --j;
+            st = (nib & 8u) ? 1 : 0;
+        } else {
+            --pos; if (out) out[pos] = '|';
+            --i;
+            st = (nib & 4u) ? 2 : 0;
+        }
+    }
+    a.path_start[p] = pos;
+    lo.start_q = i;
+    lo.start_t = j;
+    lout[pr.out] = lo;
 }
 
 // ---- sequence-store construction (K0) ----

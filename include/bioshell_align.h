@@ -25,6 +25,8 @@
  *                          bioshell-seq/examples/needleman_wunsh.rs:108-109
  *   bsa_align_pairs_paths  GlobalAligner::align + backtrace -> AlignmentPath
  *                          (global.rs:57-201, alignment_path.rs:34-48,107-115)
+ *   bsa_local_align_pairs  LocalAlignment::align + backtrace + recent_end_point (Smith-Waterman,
+ *                          SURVEY.md 8f rank 4)  bioshell-seq/src/alignment/local.rs:83-284
  *   bsa_hclust             hierarchical_clustering + HierarchicalClusteringMatrix (the consumer
  *                          of the identity matrix)
  *                          bioshell-clustering/src/hierarchical/hierarchical.rs:22-80,
@@ -144,6 +146,18 @@ int bsa_plan_shards(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_counts
 int bsa_align_pairs_paths(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_idx,
                           const uint32_t *t_idx, uint64_t n_pairs, int32_t *scores,
                           uint32_t *n_identical, uint8_t *path_buf, uint64_t *path_off);
+
+/*
+ * Local (Smith-Waterman-Gotoh) alignments for an explicit pair list, with the reference's STOP
+ * semantics and best-cell rule (local.rs:83-273).  Per pair: scores = recent_score();
+ * (end_q, end_t) = recent_end_point() (1-based cell of the best score, (0,0) if the score is 0);
+ * (start_q, start_t) and the path glyphs = backtrace().  Any output may be NULL; path_buf /
+ * path_off as in bsa_align_pairs_paths.
+ */
+int bsa_local_align_pairs(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_idx,
+                          const uint32_t *t_idx, uint64_t n_pairs, int32_t *scores, uint32_t *end_q,
+                          uint32_t *end_t, uint32_t *start_q, uint32_t *start_t, uint8_t *path_buf,
+                          uint64_t *path_off);
 
 /*
  * Hierarchical agglomerative clustering with the reference's exact merge order.

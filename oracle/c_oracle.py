@@ -26,7 +26,7 @@ class _SeqSet(C.Structure):
 
 def build(force=False):
     """Compile the C restatement with the committed recipe (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("bioshell_oracle.c", "hclust_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("bioshell_oracle.c", "hclust_oracle.c", "local_oracle.c", "Makefile")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -69,6 +69,9 @@ def lib():
         L.orc_expand_and_count.restype = C.c_int
         L.orc_hclust.argtypes = [C.c_uint32, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.orc_hclust.restype = C.c_int64
+        L.orc_local_align.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_int32)] + [C.POINTER(C.c_uint64)] * 4 + [C.c_void_p]
+        L.orc_local_align.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -213,3 +216,21 @@ def hclust(dist, rule):
     if rc < 0:
         raise OracleError(int(rc))
     return {k: v[:rc] for k, v in out.items()}
+
+
+def local_align(q, t, score, aa_index, go, ge):
+    """LocalAlignment::align + backtrace (bioshell-seq/src/alignment/local.rs:83-273) on raw bytes."""
+    q, t = bytes(q), bytes(t)
+    n, m = len(q), len(t)
+    qi = aa_index[np.frombuffer(q, np.uint8)] if n else np.zeros(1, np.uint8)
+    ti = aa_index[np.frombuffer(t, np.uint8)] if m else np.zeros(1, np.uint8)
+    qi, ti = np.ascontiguousarray(qi, np.uint8), np.ascontiguousarray(ti, np.uint8)
+    path = np.zeros(n + m + 1, np.uint8)
+    sc = C.c_int32()
+    eq, et, sq, st = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib().orc_local_align(_ptr(qi), n, _ptr(ti), m, _ptr(score), go, ge, C.byref(sc), C.byref(eq), C.byref(et),
+                               C.byref(sq), C.byref(st), _ptr(path))
+    if rc < 0:
+        raise OracleError(int(rc))
+    return dict(score=sc.value, path=path[:rc].tobytes().decode(), end_q=eq.value, end_t=et.value,
+                start_q=sq.value, start_t=st.value)

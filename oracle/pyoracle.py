@@ -157,3 +157,68 @@ def all_pairs_order(Q, T, triangle):
                 break
             out.append((q, t))
     return out
+
+
+def local_align(q, t, score, aa, go, ge):
+    """Independent restatement of LocalAlignment (bioshell-seq/src/alignment/local.rs:83-273):
+    full tables, the H selection written as the reference's three comparisons."""
+    q, t = bytes(q), bytes(t)
+    n, m = len(q), len(t)
+    H = [[0] * (m + 1) for _ in range(n + 1)]
+    E = [[0] * (m + 1) for _ in range(n + 1)]
+    F = [[0] * (m + 1) for _ in range(n + 1)]
+    arrows, et, ft = {}, {}, {}
+    recent, best = 0, (0, 0, "H")
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            ee, eo = E[i][j - 1] + ge, max(H[i][j - 1] + go, F[i][j - 1] + go)
+            if ee > 0 and ee >= eo:
+                E[i][j], et[(i, j)] = ee, 1
+            elif eo > 0:
+                E[i][j], et[(i, j)] = eo, 2
+            else:
+                E[i][j], et[(i, j)] = 0, 0
+            ff, fo = F[i - 1][j] + ge, max(H[i - 1][j] + go, E[i - 1][j] + go)
+            if ff > 0 and ff >= fo:
+                F[i][j], ft[(i, j)] = ff, 1
+            elif fo > 0:
+                F[i][j], ft[(i, j)] = fo, 2
+            else:
+                F[i][j], ft[(i, j)] = 0, 0
+            d = H[i - 1][j - 1] + score[aa[q[i - 1]] * N + aa[t[j - 1]]]
+            h, fl = 0, 0
+            for val, bit in ((d, 2), (E[i][j], 1), (F[i][j], 4)):
+                if val > h:
+                    h, fl = val, bit
+                elif val == h and h > 0:
+                    fl |= bit
+            H[i][j], arrows[(i, j)] = h, fl
+            for val, st in ((H[i][j], "H"), (E[i][j], "E"), (F[i][j], "F")):
+                if val > recent:
+                    recent, best = val, (i, j, st)
+    i, j, st = best
+    out = []
+    while True:
+        if st == "H":
+            a = arrows.get((i, j), 0)
+            if a == 0:
+                break
+            if a & 2:
+                out.append("*"); i -= 1; j -= 1
+            elif a & 1:
+                st = "E"
+            else:
+                st = "F"
+        elif st == "E":
+            tt = et.get((i, j), 0)
+            if tt == 0:
+                break
+            out.append("-"); j -= 1
+            st = "E" if tt == 1 else "H"
+        else:
+            tt = ft.get((i, j), 0)
+            if tt == 0:
+                break
+            out.append("|"); i -= 1
+            st = "F" if tt == 1 else "H"
+    return dict(score=recent, path="".join(reversed(out)), end_q=best[0], end_t=best[1], start_q=i, start_t=j)
