@@ -8,3 +8,4 @@ from .alignment import (AlignmentReporter, AlignmentStatistics, CollectReporter,
 from .scoring import SubstitutionMatrix, SubstitutionMatrixList, ncbi_text  # noqa: F401
 from .sequence import Sequence, count_identical, len_ungapped, pack, ungapped_lengths  # noqa: F401
 from . import clustering  # noqa: F401,E402
+from . import bucket_clustering  # noqa: F401,E402
