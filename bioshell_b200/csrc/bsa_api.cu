@@ -101,6 +101,7 @@ struct bsa_ctx {
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
         raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16;
     bsa_stats stats;
+    uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
 };
 
 namespace {
@@ -633,7 +634,7 @@ int bsa_load_sequences(bsa_ctx* ctx, int set_id, const uint8_t* residues_raw, co
     CK(ctx->presence.ensure(32));
     CK(cudaMemcpyAsync(S.doff.p, S.off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (total) CK(cudaMemcpyAsync(ctx->raw.p, residues_raw + base, total, cudaMemcpyHostToDevice, st));
-    ctx->stats.h2d_bytes += ((size_t)n + 1) * 8 + total;
+    ctx->pending_h2d += ((size_t)n + 1) * 8 + total;
     // which byte values occur?  (new ones get a residue code)
     CK(cudaMemsetAsync(ctx->presence.p, 0, 32, st));
     if (total) {
@@ -711,9 +712,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     const bool want_i = (flags & BSA_WANT_IDENTICAL) && n_identical;
     const bool out_dev = (flags & BSA_OUT_DEVICE) != 0;
     const int C = std::max(ctx->ncodes, 1);
-    const uint64_t h2d0 = ctx->stats.h2d_bytes;   // loads since the last call count toward it
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->stats.h2d_bytes = h2d0;
+    ctx->stats.h2d_bytes = ctx->pending_h2d;   // sequence uploads since the last call belong to this one
+    ctx->pending_h2d = 0;
 
     // ---------------- plan ----------------
     std::vector<uint64_t> first((size_t)(t_end - t_begin) + 1, 0);
@@ -1105,9 +1106,9 @@ int bsa_align_pairs_paths(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
     CK(cudaSetDevice(ctx->device));
     int rc = sync_scoring(ctx);
     if (rc) return rc;
-    const uint64_t h2d0 = ctx->stats.h2d_bytes;
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->stats.h2d_bytes = h2d0;
+    ctx->stats.h2d_bytes = ctx->pending_h2d;
+    ctx->pending_h2d = 0;
     ctx->stats.pairs = n_pairs;
     if (path_off) path_off[0] = 0;
     if (n_pairs == 0) return BSA_OK;
@@ -1198,6 +1199,8 @@ int bsa_local_align_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
     int rc = sync_scoring(ctx);
     if (rc) return rc;
     memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.h2d_bytes = ctx->pending_h2d;
+    ctx->pending_h2d = 0;
     ctx->stats.pairs = n_pairs;
     if (path_off) path_off[0] = 0;
     if (n_pairs == 0) return BSA_OK;
