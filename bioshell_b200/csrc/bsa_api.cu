@@ -99,7 +99,7 @@ struct bsa_ctx {
     SeqSet sets[kMaxSets];
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
-        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16;
+        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair;
     bsa_stats stats;
     uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
 };
@@ -134,6 +134,8 @@ typedef void (*KernelFn)(const KArgs);
 KernelFn g_stream_single[kKMax + 1], g_stream_multi[kKMax + 1], g_dirs[kKMax + 1];
 typedef void (*Kernel16Fn)(const KArgs16);
 typedef void (*KernelLocalFn)(const KArgs, LocalOut*);
+typedef void (*KernelPairFn)(const KArgsPair);
+KernelPairFn g_pair[kKMax + 1];
 KernelLocalFn g_local[kKMax + 1];
 Kernel16Fn g_score16_single[kKMax + 1], g_score16_multi[kKMax + 1];
 
@@ -144,6 +146,7 @@ struct Reg {
         g_stream_multi[K] = gotoh_stream_kernel<K, true>;
         g_score16_single[K] = gotoh_score16_kernel<K, false>;
         g_score16_multi[K] = gotoh_score16_kernel<K, true>;
+        g_pair[K] = gotoh_pair_kernel<K>;
         Reg<K - 1>::run();
     }
 };
@@ -505,7 +508,7 @@ void bsa_destroy(bsa_ctx* c) {
     for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
-                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16};
+                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -798,10 +801,63 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         }
     }
 
+    // ---- short templates: two per warp on 16 lanes each (gotoh_pair_kernel) ----
+    struct GroupPair { std::vector<Item16> items; double cells = 0, swept = 0; };
+    std::vector<GroupPair> groups_pair(kKMax + 1);
+    std::vector<uint32_t> qstart((size_t)(t_end - t_begin), 0);   // the one-template path starts here
+    if (Q.empties.empty() && !getenv("BSA_NO_PAIR")) {
+        std::vector<std::vector<uint32_t>> by_k(kKStream + 1);
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
+            const uint64_t m = T.len(t);
+            if (cnt == 0 || m == 0 || m > 16ull * kKStream || done16[t - t_begin]) continue;
+            if ((size_t)(C + 2) * ((( (m + 15) / 16) + 3) / 4) * 32 * sizeof(uint4) > kSmemBudget) continue;
+            const int cs = std::min(bitlen(m), cs_cap);
+            const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
+            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
+            const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
+                               (int64_t)std::max(-ctx->min_m, 0);
+            if (std::max(ub, lb) + 8 >= lim) continue;
+            by_k[(m + 15) / 16].push_back(t);
+        }
+        for (int K = 1; K <= kKStream; ++K) {
+            const auto& v = by_k[K];
+            for (size_t i = 0; i + 1 < v.size(); i += 2) {
+                const uint32_t tA = v[i], tB = v[i + 1];
+                const uint32_t cA = q_counts ? q_counts[tA] : Q.n, cB = q_counts ? q_counts[tB] : Q.n;
+                const uint32_t common = std::min(cA, cB);
+                const uint64_t m_pad = 32ull * K;
+                uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
+                xb = std::min<uint64_t>(xb, 1u << 18);
+                uint32_t q = 0;
+                while (q < common) {
+                    const uint64_t lim_off = Q.off[q] + xb;
+                    uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + common + 1, lim_off) -
+                                             Q.off.begin()) - 1;
+                    q2 = std::min(std::max(q2, q + 1), common);
+                    Item16 it;
+                    it.tA = tA; it.tB = tB; it.q_begin = q; it.q_end = q2;
+                    it.outA = first[tA - t_begin] + q;
+                    it.outB = first[tB - t_begin] + q;
+                    groups_pair[K].items.push_back(it);
+                    const uint64_t x = Q.off[q2] - Q.off[q];
+                    const double sw = (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
+                    padded += sw;
+                    groups_pair[K].swept += sw;
+                    groups_pair[K].cells += (double)x * (double)(T.len(tA) + T.len(tB));
+                    q = q2;
+                }
+                qstart[tA - t_begin] = common;     // what is left of the longer query list goes the usual way
+                qstart[tB - t_begin] = common;
+            }
+        }
+    }
+
     for (uint32_t t = t_begin; t < t_end; ++t) {
         const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
         if (cnt == 0) continue;
         if (done16[t - t_begin]) continue;
+        if (qstart[t - t_begin] >= cnt) continue;
         const uint64_t m = T.len(t);
         const uint64_t kbase = first[t - t_begin];
         if (m == 0) {
@@ -831,7 +887,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
 
         // runs of non-empty queries inside [0, cnt)
         auto e_it = Q.empties.begin();
-        uint32_t run_b = 0;
+        uint32_t run_b = qstart[t - t_begin];
         while (run_b < cnt) {
             while (e_it != Q.empties.end() && *e_it < run_b) ++e_it;
             uint32_t run_e = cnt;
@@ -888,9 +944,35 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     int n_groups = 0;
     for (auto& g : groups) { n_items += g.items.size(); n_groups += g.items.empty() ? 0 : 1; }
     ctx->stats.items = (uint32_t)n_items;
-    CK(ctx->counters.ensure(2 * groups.size() * 4));
+    CK(ctx->counters.ensure(3 * groups.size() * 4));
     cudaStream_t s0 = ctx->streams[0];
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 2 * groups.size() * 4, s0));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * groups.size() * 4, s0));
+    // item lists of the paired and 16-bit plans go up before the start event, so that every
+    // stream only has to wait for that one event
+    std::vector<size_t> goff_pair(groups_pair.size(), 0), goff16(groups16.size(), 0);
+    {
+        std::vector<Item16> all;
+        for (int K = kKStream; K >= 1; --K) {
+            goff_pair[K] = all.size();
+            all.insert(all.end(), groups_pair[K].items.begin(), groups_pair[K].items.end());
+        }
+        if (!all.empty()) {
+            CK(ctx->items_pair.ensure(all.size() * sizeof(Item16)));
+            CK(cudaMemcpyAsync(ctx->items_pair.p, all.data(), all.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all.size() * sizeof(Item16);
+        }
+        all.clear();
+        for (int g = (int)groups16.size() - 1; g >= 0; --g) {
+            goff16[g] = all.size();
+            all.insert(all.end(), groups16[g].items.begin(), groups16[g].items.end());
+        }
+        if (!all.empty()) {
+            CK(ctx->items16.ensure(all.size() * sizeof(Item16)));
+            CK(cudaMemcpyAsync(ctx->items16.p, all.data(), all.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all.size() * sizeof(Item16);
+        }
+        CK(cudaStreamSynchronize(s0));   // `all` is a temporary
+    }
     if (n_items) {
         std::vector<Item> all;
         all.reserve(n_items);
@@ -964,27 +1046,62 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 ++gi;
             }
         }
-        for (int i = 1; i < kStreams; ++i) {
-            CK(cudaEventRecord(ctx->ev_s[i], ctx->streams[i]));
-            CK(cudaStreamWaitEvent(s0, ctx->ev_s[i], 0));
-        }
     } else {
         CK(cudaEventRecord(ctx->ev_start, s0));
+        for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+    }
+    // ---- paired short templates ----
+    {
+        size_t np_items = 0;
+        for (auto& g : groups_pair) np_items += g.items.size();
+        if (np_items) {
+            ctx->stats.items += (uint32_t)np_items;
+            const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
+            int li = 0;
+            for (int K = kKStream; K >= 1; --K) {
+                if (groups_pair[K].items.empty()) continue;
+                KArgsPair a;
+                memset(&a, 0, sizeof(a));
+                a.Q = Q.dev(); a.T = T.dev();
+                a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
+                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.cs_cap = cs_cap;
+                a.items = ctx->items_pair.as<Item16>() + goff_pair[K];
+                a.n_items = (uint32_t)groups_pair[K].items.size();
+                a.item_counter = ctx->counters.as<uint32_t>() + 2 * groups.size() + K;
+                a.scores = d_scores; a.nident = d_nid;
+                const size_t smem = smem_for(K, C);
+                uint32_t grid = 0;
+                rc = grid_for(ctx, (KernelFn)g_pair[K], K, C, a.n_items, &grid);
+                if (rc) return rc;
+                cudaStream_t st = prof_groups ? s0 : ctx->streams[li % kStreams];
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (prof_groups) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+                g_pair[K]<<<grid, kThreads, smem, st>>>(a);
+                CK(cudaGetLastError());
+                ctx->stats.launches++;
+                if (prof_groups) {
+                    cudaEventRecord(e1, st);
+                    cudaEventSynchronize(e1);
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    fprintf(stderr, "[bsa pair ] K=%2d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n", K,
+                            groups_pair[K].items.size(), groups_pair[K].cells, groups_pair[K].swept / groups_pair[K].cells, ms,
+                            ms > 0 ? groups_pair[K].cells / 1e6 / ms : 0.0);
+                    cudaEventDestroy(e0); cudaEventDestroy(e1);
+                }
+                ++li;
+            }
+        }
     }
     // ---- 16-bit score-only groups (they follow on the same streams) ----
     {
         size_t n16 = 0;
         for (auto& g : groups16) n16 += g.items.size();
         if (n16) {
-            std::vector<Item16> all;
-            all.reserve(n16);
-            std::vector<size_t> goff(groups16.size(), 0);
             std::vector<int> gorder;
             for (int g = (int)groups16.size() - 1; g >= 0; --g) if (!groups16[g].items.empty()) gorder.push_back(g);
             uint64_t scr_total = 0;
             for (int g : gorder) {
-                goff[g] = all.size();
-                all.insert(all.end(), groups16[g].items.begin(), groups16[g].items.end());
                 if (g > kKMax) {
                     const int K = g - (kKMax + 1);
                     uint32_t grid = 0;
@@ -995,12 +1112,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 }
             }
             ctx->stats.items += (uint32_t)n16;
-            CK(ctx->items16.ensure(all.size() * sizeof(Item16)));
             if (scr_total) CK(ctx->scratch16.ensure(scr_total * sizeof(uint2)));
-            CK(cudaMemcpyAsync(ctx->items16.p, all.data(), all.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
-            ctx->stats.h2d_bytes += all.size() * sizeof(Item16);
-            CK(cudaEventRecord(ctx->ev_s[0], s0));
-            for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_s[0], 0));
             const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
             int li = 0;
             for (int g : gorder) {
@@ -1011,7 +1123,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 a.Q = Q.dev(); a.T = T.dev();
                 a.subst = ctx->d_subst.as<int16_t>();
                 a.C = C; a.go = ctx->go; a.ge = ctx->ge;
-                a.items = ctx->items16.as<Item16>() + goff[g];
+                a.items = ctx->items16.as<Item16>() + goff16[g];
                 a.n_items = (uint32_t)groups16[g].items.size();
                 a.item_counter = ctx->counters.as<uint32_t>() + groups.size() + g;
                 a.scores = d_scores;
@@ -1039,11 +1151,12 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 }
                 ++li;
             }
-            for (int i = 1; i < kStreams; ++i) {
-                CK(cudaEventRecord(ctx->ev_s[i], ctx->streams[i]));
-                CK(cudaStreamWaitEvent(s0, ctx->ev_s[i], 0));
-            }
         }
+    }
+    // one join for everything that was launched on the side streams
+    for (int i = 1; i < kStreams; ++i) {
+        CK(cudaEventRecord(ctx->ev_s[i], ctx->streams[i]));
+        CK(cudaStreamWaitEvent(s0, ctx->ev_s[i], 0));
     }
     // pairs whose score range does not fit the packed lanes: direction-store path
     if (!fallback.empty()) {

@@ -248,7 +248,9 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // intra-task wavefront).  The block to the left publishes how many boundary entries it has
 // written (`prog_out`, release store every 32 rows); this block waits on `prog_in` (acquire)
 // before it consumes them.  Without WAVE, scratch_out == scratch and the pointers are null.
-template <int K, bool DIRS, bool MULTI, bool WAVE = false, bool LOCAL = false>
+// HALF: two templates share the warp (lanes 0-15 / 16-31, see gotoh_pair_kernel); lane_last,
+// slot_last and out_idx0 are then per-lane values and positions count from the half's first lane.
+template <int K, bool DIRS, bool MULTI, bool WAVE = false, bool LOCAL = false, bool HALF = false>
 __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
                                              uint64_t g1, const uint4* prof, const uint4* rsH,
                                              const uint4* rsF, const int lane, const bool first,
@@ -268,8 +270,9 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     uint32_t avail = 0;   // WAVE: boundary entries known to be published by the left block
     constexpr int U = (DIRS || MULTI) ? 2 : (K <= 10 ? 4 : 2);
     const uint32_t X = (uint32_t)(g1 - g0);
-    const int span = (MULTI && !lastp) ? 31 : lane_last;
+    const int span = HALF ? 15 : ((MULTI && !lastp) ? 31 : lane_last);
     const uint32_t nsteps = (X + (uint32_t)span + (U - 1)) / U * U;
+    const int lrel = HALF ? (lane & 15) : lane;     // lane index inside its template
 
     int Ha[K], Hb[K], Fr[K], T[K];
     load_vec<K>(Ha, rsH + lane);
@@ -279,11 +282,11 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     int oh = 0, oe = 0;
     uint32_t emitted = 0;
     const bool border = !MULTI || first;
-    const bool lane0 = lane == 0;
+    const bool lane0 = lrel == 0;
     const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
     LaneBest lbest{0, 0u, 0u};
 
-    const uint8_t* p = codes + g0 - lane;   // lane's position at step 0 (may sit in the padding)
+    const uint8_t* p = codes + g0 - lrel;   // lane's position at step 0 (may sit in the padding)
     uint32_t b[U], nb[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
@@ -344,7 +347,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         if ((B)&kLastFlag) {                                                                      \
             /* end of a query: emit H[n][m] from the lane that owns column m, then put the */     \
             /* lane back on the top border for the next query of the stream.               */     \
-            const uint32_t pos = (S) - (uint32_t)lane;                                            \
+            const uint32_t pos = (S) - (uint32_t)lrel;                                            \
             const bool valid = pos < X;                                                           \
             if (!LOCAL && lastp && valid && lane == lane_last) {                                  \
                 int v = 0;                                                                        \
@@ -564,6 +567,25 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
 
 
 // ---------------------------------------------------------------------------------------------
+// K1 for SHORT templates (<= 16 x 20 columns): two templates of the same columns-per-lane share
+// a warp, template A on lanes 0-15 and template B on lanes 16-31, both fed by the same query
+// stream.  Each lane then owns twice as many columns as it would with one template per warp, so
+// the per-step bookkeeping (residue fetch, profile address, shuffles, border) is paid once per
+// 2K cells instead of once per K, and the column padding is cut to a 16-column granularity.
+struct KArgsPair {
+    SeqStoreDev Q, T;
+    const int16_t* subst;
+    const uint8_t* isgap;
+    int C, go, ge, one;
+    int cs_cap;             // bitlen(longest query): the count field never needs more bits
+    const struct Item16* items;
+    uint32_t n_items;
+    uint32_t* item_counter;
+    int32_t* scores;
+    uint32_t* nident;
+};
+
+// ---------------------------------------------------------------------------------------------
 // Score-only, 16-bit packed lanes (one-vs-many, BASELINE configs[3]).  Two TEMPLATES of the
 // same column count share a warp: the low and high halves of every 32-bit register carry the
 // DP values of template A and template B, both fed by the same query stream, so one
@@ -699,6 +721,104 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
 #undef BSA_STEP16
 #undef BSA_STEP16_FAST
 #undef BSA_STEP16_CORE
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kernel(const KArgsPair a) {
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_chunk;
+    constexpr int ROW = KTraits<K>::ROW;
+    uint4* prof = smem;
+    uint4* rsH = smem + (size_t)a.C * ROW;
+    uint4* rsF = rsH + ROW;
+    const int lane = threadIdx.x & 31;
+    const int lrel = lane & 15;
+    const bool isB = lane >= 16;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t ii = s_item;
+        if (ii >= a.n_items) break;
+        const Item16 it = a.items[ii];
+        const bool hasB = it.tB != 0xffffffffu;
+        const uint64_t a0 = a.T.off[it.tA];
+        const uint32_t mA = (uint32_t)(a.T.off[it.tA + 1] - a0);
+        const uint64_t b0 = hasB ? a.T.off[it.tB] : 0;
+        const uint32_t mB = hasB ? (uint32_t)(a.T.off[it.tB + 1] - b0) : 0u;
+        const uint32_t mmax = mA > mB ? mA : mB;
+        int cshift = 32 - __clz((int)mmax);
+        cshift = cshift < a.cs_cap ? cshift : a.cs_cap;
+        const Consts cs = make_consts<K>(a.go, a.ge, cshift);
+        const int S = 1 << (cs.cs + 2), P3 = 3 << cs.cs;
+
+        const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
+        const uint64_t span = x1 - x0;
+        const uint64_t head = span - span * 3 / 16;
+        const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
+        uint32_t nsmall = (uint32_t)((span - head + kChunkSmall - 1) / kChunkSmall);
+        if (nsmall < (uint32_t)kWarpsPerCta) nsmall = kWarpsPerCta;
+        const uint32_t nch = nbig + nsmall;
+
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = 0;
+        // profile: lanes 0-15 hold the columns of template A, lanes 16-31 those of template B
+        for (int idx = threadIdx.x; idx < a.C * ROW; idx += blockDim.x) {
+            const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
+            const bool b = ln >= 16;
+            const uint8_t* tc = a.T.codes + (b ? b0 : a0);
+            const uint32_t m = b ? mB : mA;
+            const bool gap = a.isgap[code] != 0;
+            int o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * v + e;
+                const uint32_t col = (uint32_t)(ln & 15) * K + c;
+                int val = cs.T_PAD;
+                if (c < K && col < m) {
+                    const int tcode = tc[col] & kCodeMask;
+                    val = (int)a.subst[code * a.C + tcode] * S + P3 + ((tcode == code && !gap) ? 1 : 0);
+                }
+                o[e] = val;
+            }
+            prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        for (int r = threadIdx.x; r < ROW; r += blockDim.x) {
+            const int v = r >> 5, ln = r & 31;
+            int h[4], f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long j = (long long)(ln & 15) * K + 4 * v + e + 1;
+                h[e] = (int)((a.go + (j - 1) * a.ge) * S);
+                f[e] = h[e] + cs.GO;
+            }
+            rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
+            rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
+        }
+        __syncthreads();
+        const uint32_t mine = isB ? mB : mA;
+        // a lane emits only for its own template; an absent template B never matches a lane
+        const int my_last = (isB && !hasB) ? -1 : (int)((mine - 1) / K) + (isB ? 16 : 0);
+        const int my_slot = mine ? (int)((mine - 1) % K) : 0;
+        const long long jl = (long long)lrel * K;
+        const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * S);
+        for (;;) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(&s_chunk, 1u);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= nch) break;
+            const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
+            const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig : head + (span - head) * (c + 1 - nbig) / nsmall;
+            const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
+            const uint32_t qb = c + 1 == nch ? it.q_end : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
+            const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+            if (g1 > g0)
+                stream_block<K, false, false, false, false, true>(
+                    a.Q.codes, g0, g1, prof, rsH, rsF, lane, true, true, my_last, my_slot, hdiag0, cs, a.one, nullptr,
+                    a.scores, a.nident, (isB ? it.outB : it.outA) + (qa - it.q_begin), nullptr);
+        }
+    }
 }
 
 struct KArgs16 {
