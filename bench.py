@@ -302,11 +302,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
                          "frac": achieved / peak_ops,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch
-                         # (gotoh_stream_kernel<9,false>, 133.8 ms, 2.9e11 cells) from the ncu --set full
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the hot kernel
+                         # family (gotoh_pair_kernel<16>, 54.1 ms, 1.2e11 cells) from the ncu --set full
                          # capture in profiles/r1_ncu_summary_final.md; algorithmic HBM bytes of that
                          # launch are ~8 B/pair of results + the 2.9 MB sequence store
-                         "traffic": 3903744,
+                         "traffic": 3046656,
                          "note": "integer/DPX issue roofline per GPU: cells/s x %.1f lane-instructions per cell vs the same "
                                  "instruction mix measured live by bsa_measure_int_peak (of measured; SM clock %.0f MHz "
                                  "during that probe). HBM is not the bound: algorithmic traffic is 8 B/pair." % (ops_per_cell, peak_mhz),
