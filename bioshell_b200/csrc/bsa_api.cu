@@ -812,10 +812,13 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             const uint64_t m = T.len(t);
             if (cnt == 0 || m == 0 || m > 16ull * kKStream || done16[t - t_begin]) continue;
             if ((size_t)(C + 2) * ((( (m + 15) / 16) + 3) / 4) * 32 * sizeof(uint4) > kSmemBudget) continue;
-            const int cs = std::min(bitlen(m), cs_cap);
+            // the kernel sizes the count field for the longer template of a pair: check with the
+            // widest field any template of this columns-per-lane class can meet
+            const uint64_t m_class = 16ull * ((m + 15) / 16);
+            const int cs = std::min(bitlen(m_class), cs_cap);
             const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
-            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
-            const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
+            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_class, Q.maxlen);
+            const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_class + 4) * (int64_t)(-ctx->ge) +
                                (int64_t)std::max(-ctx->min_m, 0);
             if (std::max(ub, lb) + 8 >= lim) continue;
             by_k[(m + 15) / 16].push_back(t);
