@@ -132,10 +132,11 @@ inline int bitlen(uint64_t x) {
 // ---------------- kernel tables ----------------
 typedef void (*KernelFn)(const KArgs);
 KernelFn g_stream_single[kKMax + 1], g_stream_multi[kKMax + 1], g_dirs[kKMax + 1];
+KernelFn g_stream_single_tag[kKMax + 1], g_stream_multi_tag[kKMax + 1];   // TAG cell (4 ALU + 3 IMAD)
 typedef void (*Kernel16Fn)(const KArgs16);
 typedef void (*KernelLocalFn)(const KArgs, LocalOut*);
 typedef void (*KernelPairFn)(const KArgsPair);
-KernelPairFn g_pair[kKMax + 1];
+KernelPairFn g_pair[kKMax + 1], g_pair_tag[kKMax + 1];
 KernelLocalFn g_local[kKMax + 1];
 Kernel16Fn g_score16_single[kKMax + 1], g_score16_multi[kKMax + 1];
 
@@ -147,6 +148,9 @@ struct Reg {
         g_score16_single[K] = gotoh_score16_kernel<K, false>;
         g_score16_multi[K] = gotoh_score16_kernel<K, true>;
         g_pair[K] = gotoh_pair_kernel<K>;
+        g_stream_single_tag[K] = gotoh_stream_kernel<K, false, true>;
+        g_stream_multi_tag[K] = gotoh_stream_kernel<K, true, true>;
+        g_pair_tag[K] = gotoh_pair_kernel<K, true>;
         Reg<K - 1>::run();
     }
 };
@@ -182,6 +186,18 @@ int k_cap(int C) {
     size_t vmax = kSmemBudget / ((size_t)(C + 2) * 32 * sizeof(uint4));
     int kc = (int)std::min<size_t>(kKMax, vmax * 4);
     return kc;
+}
+
+// stream groups are indexed K + multi * (kKMax+1) + tag * 2 (kKMax+1)
+constexpr int kGroupStride = kKMax + 1;
+inline int group_index(int K, bool multi, bool tag) { return K + (multi ? kGroupStride : 0) + (tag ? 2 * kGroupStride : 0); }
+inline int group_k(int g) { return g % kGroupStride; }
+inline bool group_multi(int g) { return (g / kGroupStride) & 1; }
+inline bool group_tag(int g) { return g >= 2 * kGroupStride; }
+inline KernelFn group_kernel(int g) {
+    const int K = group_k(g);
+    if (group_tag(g)) return group_multi(g) ? g_stream_multi_tag[K] : g_stream_single_tag[K];
+    return group_multi(g) ? g_stream_multi[K] : g_stream_single[K];
 }
 
 struct KChoice { int K; bool multi; uint32_t npass; };
@@ -429,8 +445,9 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         ta.path_start = ctx->pstart.as<uint32_t>();
         ta.nident = d_nid;
         ta.status = ctx->status.as<uint32_t>();
-        if (local) traceback_local_kernel<<<(ta.n_pairs + 63) / 64, 64, 0, st>>>(ta, d_lout);
-        else traceback_kernel<<<(ta.n_pairs + 63) / 64, 64, 0, st>>>(ta);
+        const uint32_t tb_blocks = (ta.n_pairs + kTraceThreads - 1) / kTraceThreads;
+        if (local) traceback_local_kernel<<<tb_blocks, kTraceThreads, 0, st>>>(ta, d_lout);
+        else traceback_kernel<<<tb_blocks, kTraceThreads, 0, st>>>(ta);
         CK(cudaGetLastError());
         ctx->stats.launches++;
         uint32_t status = 0;
@@ -736,7 +753,8 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
 
     const double target_cells = std::min(std::max(total_cells / 40000.0, 1048576.0), 268435456.0);
     struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0, swept = 0; };
-    std::vector<Group> groups(2 * (kKMax + 1));
+    std::vector<Group> groups(4 * kGroupStride);
+    const bool use_tag = !getenv("BSA_NO_TAG");
     std::vector<Fix> fixes;
     std::vector<PairReq> fallback;
     double padded = 0.0;
@@ -803,10 +821,10 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
 
     // ---- short templates: two per warp on 16 lanes each (gotoh_pair_kernel) ----
     struct GroupPair { std::vector<Item16> items; double cells = 0, swept = 0; };
-    std::vector<GroupPair> groups_pair(kKMax + 1);
+    std::vector<GroupPair> groups_pair(2 * kGroupStride);   // K + tag * kGroupStride
     std::vector<uint32_t> qstart((size_t)(t_end - t_begin), 0);   // the one-template path starts here
     if (Q.empties.empty() && !getenv("BSA_NO_PAIR")) {
-        std::vector<std::vector<uint32_t>> by_k(kKStream + 1);
+        std::vector<std::vector<uint32_t>> by_k(2 * kGroupStride);
         for (uint32_t t = t_begin; t < t_end; ++t) {
             const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
             const uint64_t m = T.len(t);
@@ -817,14 +835,18 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             const uint64_t m_class = 16ull * ((m + 15) / 16);
             const int cs = std::min(bitlen(m_class), cs_cap);
             const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
+            const int64_t lim_tag = cs + kTagBits <= 27 ? (int64_t)1 << (29 - cs - kTagBits) : 0;
             const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_class, Q.maxlen);
             const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_class + 4) * (int64_t)(-ctx->ge) +
                                (int64_t)std::max(-ctx->min_m, 0);
             if (std::max(ub, lb) + 8 >= lim) continue;
-            by_k[(m + 15) / 16].push_back(t);
+            const bool tag = use_tag && std::max(ub, lb) + 8 < lim_tag;
+            by_k[(m + 15) / 16 + (tag ? kGroupStride : 0)].push_back(t);
         }
-        for (int K = 1; K <= kKStream; ++K) {
-            const auto& v = by_k[K];
+        for (int gk = 1; gk < 2 * kGroupStride; ++gk) {
+            const int K = gk % kGroupStride;
+            if (K < 1 || K > kKStream) continue;
+            const auto& v = by_k[gk];
             for (size_t i = 0; i + 1 < v.size(); i += 2) {
                 const uint32_t tA = v[i], tB = v[i + 1];
                 const uint32_t cA = q_counts ? q_counts[tA] : Q.n, cB = q_counts ? q_counts[tB] : Q.n;
@@ -842,12 +864,12 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                     it.tA = tA; it.tB = tB; it.q_begin = q; it.q_end = q2;
                     it.outA = first[tA - t_begin] + q;
                     it.outB = first[tB - t_begin] + q;
-                    groups_pair[K].items.push_back(it);
+                    groups_pair[gk].items.push_back(it);
                     const uint64_t x = Q.off[q2] - Q.off[q];
                     const double sw = (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
                     padded += sw;
-                    groups_pair[K].swept += sw;
-                    groups_pair[K].cells += (double)x * (double)(T.len(tA) + T.len(tB));
+                    groups_pair[gk].swept += sw;
+                    groups_pair[gk].cells += (double)x * (double)(T.len(tA) + T.len(tB));
                     q = q2;
                 }
                 qstart[tA - t_begin] = common;     // what is left of the longer query list goes the usual way
@@ -878,10 +900,12 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         // integer-field check: score << (cs+2) must stay inside int32 for every cell
         const int cs = std::min(bitlen(m), cs_cap);
         const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
+        const int64_t lim_tag = cs + kTagBits <= 27 ? (int64_t)1 << (29 - cs - kTagBits) : 0;
         const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
         const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
                            (int64_t)std::max(-ctx->min_m, 0);
         const bool fits = std::max(ub, lb) + 8 < lim;
+        const bool fits_tag = use_tag && std::max(ub, lb) + 8 < lim_tag;   // room for the streak field too
         const uint64_t m_pad = 32ull * kc.K * kc.npass;
         uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
         // short templates: keep items small enough that their group still fills the GPU;
@@ -914,7 +938,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                     Item it;
                     it.t = t; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cs;
                     it.out_base = kbase + q;
-                    Group& grp = groups[kc.K + (kc.multi ? kKMax + 1 : 0)];
+                    Group& grp = groups[group_index(kc.K, kc.multi, fits_tag)];
                     grp.items.push_back(it);
                     const uint64_t x = Q.off[q2] - Q.off[q];
                     const double sw = (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
@@ -955,9 +979,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     std::vector<size_t> goff_pair(groups_pair.size(), 0), goff16(groups16.size(), 0);
     {
         std::vector<Item16> all;
-        for (int K = kKStream; K >= 1; --K) {
-            goff_pair[K] = all.size();
-            all.insert(all.end(), groups_pair[K].items.begin(), groups_pair[K].items.end());
+        for (int gk = (int)groups_pair.size() - 1; gk >= 0; --gk) {
+            goff_pair[gk] = all.size();
+            all.insert(all.end(), groups_pair[gk].items.begin(), groups_pair[gk].items.end());
         }
         if (!all.empty()) {
             CK(ctx->items_pair.ensure(all.size() * sizeof(Item16)));
@@ -984,7 +1008,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         std::vector<int> gorder;
         for (int g = (int)groups.size() - 1; g >= 0; --g) if (!groups[g].items.empty()) gorder.push_back(g);
         std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) {
-            return (a % (kKMax + 1)) * (a > kKMax ? 64 : 1) > (b % (kKMax + 1)) * (b > kKMax ? 64 : 1);
+            return group_k(a) * (group_multi(a) ? 64 : 1) > group_k(b) * (group_multi(b) ? 64 : 1);
         });
         for (int g : gorder) { goff[g] = all.size(); all.insert(all.end(), groups[g].items.begin(), groups[g].items.end()); }
         CK(ctx->items.ensure(all.size() * sizeof(Item)));
@@ -993,10 +1017,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         // every CTA of every concurrently running MULTI kernel owns its own boundary slice
         uint64_t scr_total = 0;
         for (int g : gorder) {
-            if (g <= kKMax) continue;
+            if (!group_multi(g)) continue;
             uint32_t grid = 0;
-            rc = grid_for(ctx, g_stream_multi[g - (kKMax + 1)], g - (kKMax + 1), C,
-                          (uint32_t)groups[g].items.size(), &grid);
+            rc = grid_for(ctx, group_kernel(g), group_k(g), C, (uint32_t)groups[g].items.size(), &grid);
             if (rc) return rc;
             groups[g].scr_off = scr_total;
             scr_total += (uint64_t)grid * groups[g].stride;
@@ -1009,13 +1032,12 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         std::vector<cudaEvent_t> pev;
         int li = 0;
         for (int g : gorder) {
-            const bool multi = g > kKMax;
-            const int K = multi ? g - (kKMax + 1) : g;
+            const int K = group_k(g);
             KArgs a;
             memset(&a, 0, sizeof(a));
             a.Q = Q.dev(); a.T = T.dev();
             a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1;
             a.items = ctx->items.as<Item>() + goff[g];
             a.n_items = (uint32_t)groups[g].items.size();
             a.item_counter = ctx->counters.as<uint32_t>() + g;
@@ -1026,11 +1048,11 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0); cudaEventCreate(&e1);
                 cudaEventRecord(e0, s0);
-                rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, s0);
+                rc = launch(ctx, group_kernel(g), K, a, s0);
                 cudaEventRecord(e1, s0);
                 pev.push_back(e0); pev.push_back(e1);
             } else {
-                rc = launch(ctx, multi ? g_stream_multi[K] : g_stream_single[K], K, a, ctx->streams[li % kStreams]);
+                rc = launch(ctx, group_kernel(g), K, a, ctx->streams[li % kStreams]);
             }
             if (rc) return rc;
             ++li;
@@ -1041,8 +1063,8 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             for (int g : gorder) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, pev[2 * gi], pev[2 * gi + 1]);
-                fprintf(stderr, "[bsa group] K=%2d multi=%d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n",
-                        g > kKMax ? g - (kKMax + 1) : g, g > kKMax ? 1 : 0, groups[g].items.size(), groups[g].cells,
+                fprintf(stderr, "[bsa group] K=%2d multi=%d tag=%d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n",
+                        group_k(g), group_multi(g) ? 1 : 0, group_tag(g) ? 1 : 0, groups[g].items.size(), groups[g].cells,
                         groups[g].cells > 0 ? groups[g].swept / groups[g].cells : 0.0, ms,
                         ms > 0 ? groups[g].cells / 1e6 / ms : 0.0);
                 cudaEventDestroy(pev[2 * gi]); cudaEventDestroy(pev[2 * gi + 1]);
@@ -1061,25 +1083,28 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             ctx->stats.items += (uint32_t)np_items;
             const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
             int li = 0;
-            for (int K = kKStream; K >= 1; --K) {
-                if (groups_pair[K].items.empty()) continue;
+            for (int gk = (int)groups_pair.size() - 1; gk >= 0; --gk) {
+                if (groups_pair[gk].items.empty()) continue;
+                const int K = gk % kGroupStride;
+                const bool tag = gk >= kGroupStride;
+                const KernelPairFn pfn = tag ? g_pair_tag[K] : g_pair[K];
                 KArgsPair a;
                 memset(&a, 0, sizeof(a));
                 a.Q = Q.dev(); a.T = T.dev();
                 a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.cs_cap = cs_cap;
-                a.items = ctx->items_pair.as<Item16>() + goff_pair[K];
-                a.n_items = (uint32_t)groups_pair[K].items.size();
-                a.item_counter = ctx->counters.as<uint32_t>() + 2 * groups.size() + K;
+                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1; a.cs_cap = cs_cap;
+                a.items = ctx->items_pair.as<Item16>() + goff_pair[gk];
+                a.n_items = (uint32_t)groups_pair[gk].items.size();
+                a.item_counter = ctx->counters.as<uint32_t>() + 2 * groups.size() + gk;
                 a.scores = d_scores; a.nident = d_nid;
                 const size_t smem = smem_for(K, C);
                 uint32_t grid = 0;
-                rc = grid_for(ctx, (KernelFn)g_pair[K], K, C, a.n_items, &grid);
+                rc = grid_for(ctx, (KernelFn)pfn, K, C, a.n_items, &grid);
                 if (rc) return rc;
                 cudaStream_t st = prof_groups ? s0 : ctx->streams[li % kStreams];
                 cudaEvent_t e0 = nullptr, e1 = nullptr;
                 if (prof_groups) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-                g_pair[K]<<<grid, kThreads, smem, st>>>(a);
+                pfn<<<grid, kThreads, smem, st>>>(a);
                 CK(cudaGetLastError());
                 ctx->stats.launches++;
                 if (prof_groups) {
@@ -1087,9 +1112,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                     cudaEventSynchronize(e1);
                     float ms = 0.f;
                     cudaEventElapsedTime(&ms, e0, e1);
-                    fprintf(stderr, "[bsa pair ] K=%2d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n", K,
-                            groups_pair[K].items.size(), groups_pair[K].cells, groups_pair[K].swept / groups_pair[K].cells, ms,
-                            ms > 0 ? groups_pair[K].cells / 1e6 / ms : 0.0);
+                    fprintf(stderr, "[bsa pair ] K=%2d tag=%d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n", K,
+                            tag ? 1 : 0, groups_pair[gk].items.size(), groups_pair[gk].cells,
+                            groups_pair[gk].swept / groups_pair[gk].cells, ms, ms > 0 ? groups_pair[gk].cells / 1e6 / ms : 0.0);
                     cudaEventDestroy(e0); cudaEventDestroy(e1);
                 }
                 ++li;

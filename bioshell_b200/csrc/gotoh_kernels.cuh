@@ -84,6 +84,7 @@ struct KArgs {
     int C;
     int go, ge;
     int one;                // the constant 1, kept opaque to the compiler (see cell_row)
+    int one2;               // a second one (TAG cell: keeps the two openings apart)
     const Item* items;
     uint32_t n_items;
     uint32_t* item_counter;
@@ -109,10 +110,25 @@ __device__ __forceinline__ int addmax_s32(int a, int b, int c) { return __viaddm
 
 struct Consts {
     int GE, GO, MASK, PH, PV, T_PAD;
+    int GEB;  // border step gap_extend << sh (GE also carries the streak increment in TAG mode)
+    int GOE, GOF;  // TAG: gap_open with the E / F priority already in place (== GO otherwise)
+    int XCLR;      // TAG: clears the streak field
     int hb0;  // packed H[1][0] = gap_open
-    int cs;
+    int cs;   // width of the count field
+    int ps;   // position of the 2-bit priority field (cs, or cs + kTagBits in TAG mode)
+    int sh;   // position of the score field (ps + 2)
     bool local;   // Smith-Waterman borders: everything starts at 0
 };
+
+// TAG cell (score + identity kernels): width of the streak field x that sits between the count
+// and the priority,   v = score << (cs+7) | prio << (cs+5) | x << cs | count.
+// E and F values are born with their H-max priority (2 / 1) already in place, so the two
+// `| PH`, `| PV` of the classic cell disappear; "extend beats open on ties" (global.rs:109,122)
+// comes from x: an extension adds 1 to x, an opening has x = 0.  x only matters in the one
+// comparison that follows the increment, so it is simply cleared when E enters the next lane
+// (<= K <= 20 increments) and every kTagRows rows for F: it never reaches 2^kTagBits.
+constexpr int kTagBits = 5;
+constexpr uint32_t kTagRows = 16;
 
 template <int K>
 struct KTraits {
@@ -135,8 +151,8 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
                                               uint32_t colbase, const KArgs& a, const Consts& cs) {
     constexpr int ROW = KTraits<K>::ROW;
     const int C = a.C;
-    const int S = 1 << (cs.cs + 2);
-    const int P3 = 3 << cs.cs;
+    const int S = 1 << cs.sh;
+    const int P3 = 3 << cs.ps;
     for (int idx = threadIdx.x; idx < C * ROW; idx += blockDim.x) {
         const int code = idx / ROW;
         const int r = idx - code * ROW;
@@ -168,7 +184,7 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
             const long long j = (long long)colbase + lane * K + c + 1;  // DP column
             const int hv = cs.local ? 0 : (int)((a.go + (j - 1) * a.ge) * S);
             h[e] = hv;
-            f[e] = cs.local ? 0 : hv + cs.GO;
+            f[e] = cs.local ? 0 : hv + cs.GOF;
         }
         rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
         rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -196,10 +212,27 @@ __device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict_
 // LOCAL (Smith-Waterman, bioshell-seq/src/alignment/local.rs:120-203): the same recurrences
 // with the three maxima clamped at zero (the DPX *_relu forms).  A value whose score field is
 // <= 0 is the reference's STOP: it carries direction 0 and clears to exactly 0 under MASK.
-template <int K, bool DIRS, bool LOCAL = false>
+template <int K, bool DIRS, bool LOCAL = false, bool TAG = false>
 __device__ __forceinline__ void cell_row(const int (&Hold)[K], int (&Hnew)[K], int (&Fr)[K],
                                          const int (&T)[K], int hd, int& er, const Consts& cs,
-                                         const int one, uint32_t (&dw)[KTraits<K>::W], int& rowmax) {
+                                         const int one, const int one2, uint32_t (&dw)[KTraits<K>::W],
+                                         int& rowmax) {
+    if constexpr (TAG) {
+        // 4 ALU-pipe instructions (VIMNMX3, LOP3, 2 VIADDMNMX) + 3 IMAD; `one` and `one2` are two
+        // separate runtime 1s so that the two openings stay two IMADs (no shared product + IADD3)
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+            const int d = hd * one + T[c];
+            const int h = max3_s32(d, er, Fr[c]);
+            const int hc = h & cs.MASK;
+            const int hge = hc * one + cs.GOE;
+            const int hgf = hc * one2 + cs.GOF;
+            er = addmax_s32(er, cs.GE, hge);
+            Fr[c] = addmax_s32(Fr[c], cs.GE, hgf);
+            hd = Hold[c];
+            Hnew[c] = hc;
+        }
+    } else {
 #pragma unroll
     for (int c = 0; c < K; ++c) {
         const int e = er | cs.PH;
@@ -219,6 +252,7 @@ __device__ __forceinline__ void cell_row(const int (&Hold)[K], int (&Hnew)[K], i
         if (LOCAL) rowmax = rowmax > hc ? rowmax : hc;
         hd = Hold[c];
         Hnew[c] = hc;
+    }
     }
 }
 
@@ -250,7 +284,8 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // before it consumes them.  Without WAVE, scratch_out == scratch and the pointers are null.
 // HALF: two templates share the warp (lanes 0-15 / 16-31, see gotoh_pair_kernel); lane_last,
 // slot_last and out_idx0 are then per-lane values and positions count from the half's first lane.
-template <int K, bool DIRS, bool MULTI, bool WAVE = false, bool LOCAL = false, bool HALF = false>
+template <int K, bool DIRS, bool MULTI, bool WAVE = false, bool LOCAL = false, bool HALF = false,
+          bool TAG = false>
 __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
                                              uint64_t g1, const uint4* prof, const uint4* rsH,
                                              const uint4* rsF, const int lane, const bool first,
@@ -263,7 +298,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                                              uint32_t* __restrict__ dirs, uint2* scratch_out = nullptr,
                                              const uint32_t* prog_in = nullptr,
                                              uint32_t* prog_out = nullptr, LaneBest* lane_best = nullptr,
-                                             const uint32_t colbase = 0) {
+                                             const uint32_t colbase = 0, const int one2 = 1) {
+    static_assert(!TAG || (!DIRS && !LOCAL && !WAVE), "the TAG cell carries no direction bits");
     constexpr int W = KTraits<K>::W;
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
     if (!WAVE) scratch_out = scratch;
@@ -305,20 +341,21 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         if (lane0) {                                                                              \
             if (border) { /* H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101) */ \
                 hin = LOCAL ? 0 : hb;            /* local: H[i][0] = E[i][1] = 0 (local.rs:116) */ \
-                er = LOCAL ? 0 : hb + cs.GO;                                                      \
+                er = LOCAL ? 0 : hb + cs.GOE;                                                     \
             } else {                                                                              \
                 hin = (int)sc_next.x;                                                             \
                 er = (int)sc_next.y;                                                              \
             }                                                                                     \
         }                                                                                         \
+        if (TAG) er &= cs.XCLR;   /* the streak restarts in every lane */                         \
         if (MULTI && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];                  \
-        hb += cs.GE;                                                                              \
+        hb += cs.GEB;                                                                             \
         const int hd = hdiag;                                                                     \
         hdiag = hin;                                                                              \
         uint32_t dw[W];                                                                           \
         _Pragma("unroll") for (int w = 0; w < W; ++w) dw[w] = 0u;                                 \
         int rowmax = 0;                                                                           \
-        cell_row<K, DIRS, LOCAL>(HO, HN, Fr, T, hd, er, cs, one, dw, rowmax);                     \
+        cell_row<K, DIRS, LOCAL, TAG>(HO, HN, Fr, T, hd, er, cs, one, one2, dw, rowmax);                     \
         if (LOCAL && rowmax > lbest.v && (S) - (uint32_t)lane < X) {                              \
             /* a new best in this lane: remember the row and the first column that holds it */   \
             lbest.v = rowmax;                                                                     \
@@ -353,7 +390,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                 int v = 0;                                                                        \
                 _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = HN[c];      \
                 const uint64_t k = out_idx0 + emitted;                                            \
-                if (scores) scores[k] = v >> (cs.cs + 2);                                         \
+                if (scores) scores[k] = v >> cs.sh;                                               \
                 if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                       \
             }                                                                                     \
             emitted += valid ? 1u : 0u;                                                           \
@@ -372,6 +409,10 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                 if (lane0) while ((avail = ld_acquire_u32(prog_in)) < need) {}
                 avail = __shfl_sync(0xffffffffu, avail, 0);
             }
+        }
+        if (TAG && (s & (kTagRows - 1u)) == 0u) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) Fr[c] &= cs.XCLR;
         }
         uint32_t any = 0;
 #pragma unroll
@@ -413,19 +454,27 @@ __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__
 }
 
 template <int K>
-__device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool local = false) {
+__device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool local = false,
+                                              bool tag = false) {
     Consts cs;
     cs.cs = cshift;
-    const int S = 1 << (cshift + 2);
-    cs.GE = ge * S;
+    cs.ps = cshift + (tag ? kTagBits : 0);
+    cs.sh = cs.ps + 2;
+    const int S = 1 << cs.sh;
+    const int xmask = tag ? ((1 << kTagBits) - 1) << cshift : 0;
+    cs.GEB = ge * S;
+    cs.GE = ge * S + (tag ? 1 << cshift : 0);
     cs.GO = go * S;
-    cs.MASK = ~(3 << cshift);
-    cs.PH = 2 << cshift;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
-    cs.PV = 1 << cshift;   // F: vertical, gap in the template
+    cs.MASK = ~((3 << cs.ps) | xmask);
+    cs.XCLR = ~xmask;
+    cs.PH = 2 << cs.ps;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
+    cs.PV = 1 << cs.ps;   // F: vertical, gap in the template
+    cs.GOE = cs.GO + (tag ? cs.PH : 0);
+    cs.GOF = cs.GO + (tag ? cs.PV : 0);
     // padded columns: neutral in global mode; in local mode they must never score, so that no
     // cell outside the template can reach the best score (anything they inherit through E/F is
     // strictly below a real cell of the same row)
-    cs.T_PAD = local ? -(1 << 24) : 3 << cshift;
+    cs.T_PAD = local ? -(1 << 24) : 3 << cs.ps;
     cs.hb0 = go * S;
     cs.local = local;
     return cs;
@@ -442,7 +491,7 @@ struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= 12 ? 3 : 2); 
 constexpr uint32_t kChunkBig = 4096;    // stream residues per chunk (pipeline fill is 31 steps)
 constexpr uint32_t kChunkSmall = 640;
 
-template <int K, bool MULTI>
+template <int K, bool MULTI, bool TAG = false>
 __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_kernel(const KArgs a) {
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_item;
@@ -462,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
         const uint64_t t0 = a.T.off[it.t];
         const uint32_t m = (uint32_t)(a.T.off[it.t + 1] - t0);
         const uint8_t* tc = a.T.codes + t0;
-        const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift);
+        const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift, false, TAG);
 
         // chunk schedule: big chunks over the first 13/16 of the stream, small ones over the rest,
         // so the warps reach the item's closing barrier within half a small chunk of each other
@@ -487,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
             const int lane_last = (int)((m - 1 - colbase) / K);
             const int slot_last = (int)((m - 1 - colbase) % K);
             const long long jl = (long long)colbase + (long long)lane * K;  // DP column left of the lane
-            const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * (1 << (cs.cs + 2)));
+            const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * (1 << cs.sh));
             for (;;) {
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(&s_chunk, 1u);
@@ -502,10 +551,10 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
                                                  : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
                 const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
                 if (g1 > g0)
-                    stream_block<K, false, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0,
-                                                  lastp, lastp ? lane_last : 31, slot_last, hdiag0, cs,
-                                                  a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
-                                                  a.nident, it.out_base + (qa - it.q_begin), nullptr);
+                    stream_block<K, false, MULTI, false, false, false, TAG>(
+                        a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp, lastp ? lane_last : 31,
+                        slot_last, hdiag0, cs, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores, a.nident,
+                        it.out_base + (qa - it.q_begin), nullptr, nullptr, nullptr, nullptr, nullptr, 0, a.one2);
             }
         }
     }
@@ -576,7 +625,7 @@ struct KArgsPair {
     SeqStoreDev Q, T;
     const int16_t* subst;
     const uint8_t* isgap;
-    int C, go, ge, one;
+    int C, go, ge, one, one2;
     int cs_cap;             // bitlen(longest query): the count field never needs more bits
     const struct Item16* items;
     uint32_t n_items;
@@ -723,7 +772,7 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
 #undef BSA_STEP16_CORE
 }
 
-template <int K>
+template <int K, bool TAG = false>
 __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kernel(const KArgsPair a) {
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_item;
@@ -750,8 +799,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const uint32_t mmax = mA > mB ? mA : mB;
         int cshift = 32 - __clz((int)mmax);
         cshift = cshift < a.cs_cap ? cshift : a.cs_cap;
-        const Consts cs = make_consts<K>(a.go, a.ge, cshift);
-        const int S = 1 << (cs.cs + 2), P3 = 3 << cs.cs;
+        const Consts cs = make_consts<K>(a.go, a.ge, cshift, false, TAG);
+        const int S = 1 << cs.sh, P3 = 3 << cs.ps;
 
         const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
         const uint64_t span = x1 - x0;
@@ -791,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             for (int e = 0; e < 4; ++e) {
                 const long long j = (long long)(ln & 15) * K + 4 * v + e + 1;
                 h[e] = (int)((a.go + (j - 1) * a.ge) * S);
-                f[e] = h[e] + cs.GO;
+                f[e] = h[e] + cs.GOF;
             }
             rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
             rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -814,9 +863,10 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             const uint32_t qb = c + 1 == nch ? it.q_end : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
             const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
             if (g1 > g0)
-                stream_block<K, false, false, false, false, true>(
+                stream_block<K, false, false, false, false, true, TAG>(
                     a.Q.codes, g0, g1, prof, rsH, rsF, lane, true, true, my_last, my_slot, hdiag0, cs, a.one, nullptr,
-                    a.scores, a.nident, (isB ? it.outB : it.outA) + (qa - it.q_begin), nullptr);
+                    a.scores, a.nident, (isB ? it.outB : it.outA) + (qa - it.q_begin), nullptr, nullptr, nullptr,
+                    nullptr, nullptr, 0, a.one2);
         }
     }
 }
@@ -1030,6 +1080,33 @@ struct TraceArgs {
     uint32_t* status;       // set to 1 if an invalid direction is met
 };
 
+// The walk mostly moves diagonally, i.e. one step (a new 128-byte line) back per glyph, and
+// every load depends on the previous one.  DirWindow keeps, per thread, the direction words of the
+// current (pass, lane, word) column for the last kTraceWin steps: a refill issues kTraceWin
+// independent loads at once, so the DRAM/L2 latency is paid once per kTraceWin glyphs.
+constexpr int kTraceWin = 16;
+constexpr int kTraceThreads = 64;
+
+struct DirWindow {
+    uint32_t key = 0xffffffffu, top = 0;
+    __device__ __forceinline__ uint32_t get(uint32_t* win, const uint32_t* __restrict__ dirs, size_t plane,
+                                            uint32_t W, uint32_t pass, uint32_t step, uint32_t lane, uint32_t w) {
+        const uint32_t k = (pass * 32u + lane) * 4u + w;
+        if (k != key || step > top || step + kTraceWin <= top) {
+            key = k;
+            top = step;
+            const uint32_t* base = dirs + pass * plane + (size_t)lane * W + w;
+            uint32_t v[kTraceWin];
+#pragma unroll
+            for (int d = 0; d < kTraceWin; ++d)
+                v[d] = (uint32_t)d <= step ? base[(size_t)(step - d) * 32 * W] : 0u;
+#pragma unroll
+            for (int d = 0; d < kTraceWin; ++d) win[d] = v[d];
+        }
+        return win[top - step];
+    }
+};
+
 __global__ void traceback_kernel(const TraceArgs a) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.n_pairs) return;
@@ -1044,13 +1121,15 @@ __global__ void traceback_kernel(const TraceArgs a) {
     uint8_t* out = a.path ? a.path + pr.path_off : nullptr;
     uint32_t pos = n + m, i = n, j = m, nid = 0;
     int st = 0;
+    __shared__ uint32_t s_win[kTraceThreads][kTraceWin + 1];
+    DirWindow dw;
     while (i > 0 && j > 0) {
         const uint32_t col = j - 1, pass = col / BK, lc = col - pass * BK;
         const uint32_t lane = lc / K, c = lc - lane * K;
         const uint32_t step = (i - 1) + lane, w = c >> 3;
         const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
         const uint32_t sh = 4 * (cnt - 1 - (c & 7));
-        const uint32_t nib = (dirs[pass * plane + ((size_t)step * 32 + lane) * W + w] >> sh) & 15u;
+        const uint32_t nib = (dw.get(s_win[threadIdx.x], dirs, plane, W, pass, step, lane, w) >> sh) & 15u;
         if (st == 0) {
             const uint32_t hd = nib & 3u;
             if (hd == 3u) {
@@ -1172,13 +1251,15 @@ __global__ void traceback_local_kernel(const TraceArgs a, LocalOut* __restrict__
     LocalOut lo = lout[pr.out];
     uint32_t pos = n + m, i = lo.end_q, j = lo.end_t;
     int st = 0;
+    __shared__ uint32_t s_win[kTraceThreads][kTraceWin + 1];
+    DirWindow dw;
     while (i > 0 && j > 0) {
         const uint32_t col = j - 1, pass = col / BK, lc = col - pass * BK;
         const uint32_t lane = lc / K, c = lc - lane * K;
         const uint32_t step = (i - 1) + lane, w = c >> 3;
         const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
         const uint32_t sh = 4 * (cnt - 1 - (c & 7));
-        const uint32_t nib = (dirs[pass * plane + ((size_t)step * 32 + lane) * W + w] >> sh) & 15u;
+        const uint32_t nib = (dw.get(s_win[threadIdx.x], dirs, plane, W, pass, step, lane, w) >> sh) & 15u;
         if (st == 0) {
             const uint32_t hd = nib & 3u;
             if (hd == 0u) break;                                   // arrows == 0: STOP

@@ -68,3 +68,53 @@ def walk_dirs(n, m, dirs):
     out.extend("-" * j)
     out.extend("|" * i)
     return "".join(reversed(out))
+
+
+def tagged_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
+    """Model of the TAG cell (gotoh_kernels.cuh, cell_row_tag): the E/F values keep their H-max
+    priority for good (opened from H with prio 2 / 1 already in place) and the extend-beats-open
+    tie rule (global.rs:109,122) comes from a STREAK field x below the priority: an extension
+    adds 1 to x, an opening has x = 0.  x only matters in the comparison that follows the
+    increment, so it is simply cleared when E enters the next lane (every K columns) and every R
+    rows for F -- it never reaches 2**xb.   v = score << (cs+xb+2) | prio << (cs+xb) | x << cs | count
+    4 ALU-pipe instructions per cell (VIMNMX3, LOP3, 2 VIADDMNMX) + 3 IMAD."""
+    n, m = len(q), len(t)
+    U, X1 = 1 << cs, 1 << cs
+    P1 = 1 << (cs + xb)
+    S = 1 << (cs + xb + 2)
+    XMASK = ((1 << xb) - 1) << cs
+    MASK = ~(3 * P1 | XMASK)
+    GEX = ge * S + X1
+    GOE, GOF = go * S + 2 * P1, go * S + P1
+    gaps = (ord("-"), ord("_"))
+
+    def T(a, b):
+        ident = 1 if (cs > 0 and a == b and a not in gaps) else 0
+        return score[aa[a] * 21 + aa[b]] * S + 3 * P1 + ident
+
+    Hc = [(go + j * ge) * S for j in range(m)]
+    Fr = [h + GOF for h in Hc]
+    hb = go * S
+    for i in range(n):
+        if i % R == 0:
+            Fr = [f & ~XMASK for f in Fr]
+        hin, er = hb, hb + GOE
+        hb += ge * S
+        hd = 0 if i == 0 else (go + (i - 1) * ge) * S
+        for c in range(m):
+            if c % K == 0:
+                er &= ~XMASK                      # lane boundary: after the shuffle
+            d = hd + T(q[i], t[c])
+            h = max(d, er, Fr[c])
+            hc = h & MASK
+            er = max(er + GEX, hc + GOE)
+            Fr[c] = max(Fr[c] + GEX, hc + GOF)
+            assert (er & XMASK) >> cs <= K and (Fr[c] & XMASK) >> cs <= R
+            assert (er >> (cs + xb)) & 3 == 2 and (Fr[c] >> (cs + xb)) & 3 == 1
+            hd, Hc[c] = Hc[c], hc
+    if m == 0:
+        v = 0 if n == 0 else (go + (n - 1) * ge) * S
+    else:
+        v = Hc[m - 1]
+    assert -(1 << 31) <= v < (1 << 31)
+    return v >> (cs + xb + 2), v & (U - 1)

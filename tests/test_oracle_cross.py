@@ -7,7 +7,7 @@ import pytest
 
 from bioshell_b200.scoring import ncbi_text
 from oracle import c_oracle, pyoracle
-from packed_model import packed_align, walk_dirs
+from packed_model import packed_align, tagged_align, walk_dirs
 
 AA = b"ARNDCQEGHILKMFPSTWYV"
 DIRTY = b"ARNDCQEGHILKMFPSTWYVXBZJUO*-_arndx"
@@ -77,6 +77,27 @@ def test_packed_lane_model_matches_oracle(alphabet):
         s0, _, dirs = packed_align(q, t, psc, pai, go, ge, 0, want_dirs=True)
         assert s0 == ref["score"]
         assert walk_dirs(len(q), len(t), dirs) == ref["path"], (q, t, go, ge)
+
+
+@pytest.mark.parametrize("alphabet", [AA, DIRTY])
+def test_tagged_lane_model_matches_oracle(alphabet):
+    """The TAG cell (4 ALU + 3 IMAD: priorities born in place, extend-beats-open through a streak
+    field that is cleared at lane boundaries / every R rows) gives the reference's score and
+    n_identical for every lane width and clearing period, including the degenerate ones."""
+    text = ncbi_text("BLOSUM62")
+    sc, ai = c_oracle.parse_ncbi(text)
+    psc, pai = pyoracle.parse_ncbi(text)
+    k = 0
+    for q, t in pairs(29, 400, 48, alphabet):
+        go, ge = GAPS[k % len(GAPS)]
+        k += 1
+        if ge == 0 and max(len(q), len(t)) < 2:
+            continue
+        ref = c_oracle.align_pair(q, t, sc, ai, go, ge, max(len(q), len(t)) + 100 * (k % 3))
+        cs = max(len(q), len(t)).bit_length()
+        for K, R, xb in ((4, 16, 5), (1, 1, 1), (20, 16, 5), (3, 5, 3)):
+            s, nid = tagged_align(q, t, psc, pai, go, ge, cs, xb=xb, K=K, R=R)
+            assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R)
 
 
 def test_orientation_matters_for_identity_not_score():
