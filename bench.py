@@ -11,8 +11,8 @@ every pair of the upper triangle) over one synthetic protein set.
   e2e     the same metric through the reference-facing call with HOST buffers: every step
           uploads the raw residues from pinned host memory (bsa_load_sequences), aligns, and
           copies scores + identical counts back to pinned host memory; wall clock.
-  roofline  integer-ALU/DPX bound: achieved = cells/s x 8 lane-instructions
-          per cell (the kernel's packed cell) against the lane-op rate of the same
+  roofline  integer-ALU/DPX bound: achieved = cells/s x 7 lane-instructions
+          per cell (the kernel's TAG cell) against the lane-op rate of the same
           instruction mix measured live on this GPU by bsa_measure_int_peak.
   cpu_baseline  the oracle (literal C port of the reference path) on the host cores, on a
           bounded random sample of the same workload's pairs.
@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-OPS_PER_CELL = 8          # lane-instructions of the packed cell (gotoh_kernels.cuh header)
+OPS_PER_CELL = 7          # lane-instructions of the TAG cell: 4 ALU-pipe + 3 IMAD (gotoh_kernels.cuh)
 MATRIX, GO, GE = "BLOSUM62", -10, -1
 
 
@@ -202,7 +202,7 @@ def main():
         counts = None
         ctx.load_sequences(1, qres, qoff)
         ctx.load_sequences(0, res, off)
-        q_set, ops_per_cell, peak_which, want_i = 1, 2.5, 6, False
+        q_set, ops_per_cell, peak_which, want_i = 1, 2.0, 6, False   # 4 ALU-pipe instr per TWO cells (+1 IMAD)
         bounds = ctx.plan_shards(1, 0, None, world)
         t0, t1 = int(bounds[rank]), int(bounds[rank + 1])
         n_res = (t1 - t0) * (len(qoff) - 1)
@@ -211,7 +211,7 @@ def main():
         n = len(off) - 1
         counts = np.arange(n, dtype=np.uint32)
         ctx.load_sequences(0, res, off)
-        q_set, ops_per_cell, peak_which, want_i = 0, OPS_PER_CELL, 0, True
+        q_set, ops_per_cell, peak_which, want_i = 0, OPS_PER_CELL, 7, True
         bounds = ctx.plan_shards(0, 0, counts, world)          # identical on every rank: no exchange
         t0, t1 = int(bounds[rank]), int(bounds[rank + 1])
         n_res = int(counts[t0:t1].astype(np.int64).sum())

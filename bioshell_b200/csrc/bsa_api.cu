@@ -773,9 +773,12 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             if (cnt == 0 || m == 0) continue;
             const KChoice kc = choose_k(m, C);
             if (kc.K < 1) continue;
-            // every DP value (incl. borders and E/F one step below them) must fit a signed 16-bit lane
-            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
-            const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
+            // every DP value (incl. borders, E/F one step below them, and the padded columns of the
+            // shorter template of a pair) must fit a 16-bit lane; the biased low half must also stay
+            // >= |go| so that the 32-bit `h + GO` never borrows from the high half
+            const uint64_t m_pad16 = 32ull * kc.K * kc.npass;
+            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_pad16, Q.maxlen);
+            const int64_t lb = 5 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_pad16 + 68) * (int64_t)(-ctx->ge) +
                                (int64_t)std::max(-ctx->min_m, 0);
             if (std::max(ub, lb) >= 32000) continue;
             cands.push_back(Cand{t, cnt, m, kc.K + (kc.multi ? kKMax + 1 : 0) + (int)kc.npass * 256});
@@ -1150,7 +1153,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 memset(&a, 0, sizeof(a));
                 a.Q = Q.dev(); a.T = T.dev();
                 a.subst = ctx->d_subst.as<int16_t>();
-                a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
                 a.items = ctx->items16.as<Item16>() + goff16[g];
                 a.n_items = (uint32_t)groups16[g].items.size();
                 a.item_counter = ctx->counters.as<uint32_t>() + groups.size() + g;

@@ -443,6 +443,165 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     if (LOCAL) *lane_best = lbest;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TWO ROWS PER STEP (TAG cell, one column block, score + identity).  The dependency chain of a
+// row is four instructions per cell (VIMNMX3 -> LOP3 -> IMAD -> VIADDMNMX) and with 8-16 warps
+// per SM the ALU pipe waits on it.  Here the lanes are skewed by TWO stream positions: at double
+// step S lane l works on rows 2(S-l) and 2(S-l)+1, cell (r+1, c) right after cell (r, c), so the
+// warp always has two independent chains in flight.  H is updated in place (one array: the
+// diagonal values travel in two scalars), the two profile rows take the registers the ping-pong
+// copy of H used to take.  A double step in which some lane passes an end-of-sequence flag runs
+// its two rows one after the other with the flag handling in between.
+// Which column counts take the two-row step: measured per K on B200 (gpurun_out/qb_groups_tag*.log);
+// where the register budget forces spills (K = 11, 12 at three CTAs per SM, K = 19/20) the
+// one-row step is as fast or faster.
+template <int K, bool HALF>
+struct TwoRows {
+    static constexpr bool value = HALF ? (K >= 8 && K != 11 && K != 12 && K != 19) : (K >= 13 && K <= 19);
+};
+
+template <int K, bool HALF>
+__device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ codes, uint64_t g0, uint64_t g1,
+                                                  const uint4* prof, const uint4* rsH, const uint4* rsF,
+                                                  const int lane, const int lane_last, const int slot_last,
+                                                  const int hdiag0, const Consts cs, const int one, const int one2,
+                                                  int32_t* __restrict__ scores, uint32_t* __restrict__ nident,
+                                                  uint64_t out_idx0) {
+    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int U = K <= 10 ? 2 : 1;          // double steps per loop iteration
+    static_assert(8 % U == 0, "the F streak is cleared every 8 double steps");
+    const uint32_t X = (uint32_t)(g1 - g0);
+    const int span = HALF ? 15 : lane_last;
+    const uint32_t nd = ((X + 1u) / 2u + (uint32_t)span + (U - 1)) / U * U;
+    const int lrel = HALF ? (lane & 15) : lane;
+    const bool lane0 = lrel == 0;
+
+    int H[K], Fr[K], T0[K], T1[K];
+    load_vec<K>(H, rsH + lane);
+    load_vec<K>(Fr, rsF + lane);
+    int hdiag = hdiag0, hb = cs.hb0;
+    int oh0 = 0, oe0 = 0, oh1 = 0, oe1 = 0;
+    uint32_t emitted = 0;
+    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
+    const uint8_t* p = codes + g0 - 2 * lrel;   // lane's first row at double step 0 (may sit in the padding)
+    uint32_t b[2 * U], nb[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) b[u] = ld_code(p + u);
+
+    // one row, in place (the checked path)
+#define BSA_ROW1(TT, HIN, ER, OH, OE)                                                             \
+    {                                                                                             \
+        if (lane0) { HIN = hb; ER = hb + cs.GOE; }                                                \
+        hb += cs.GEB;                                                                             \
+        ER &= cs.XCLR;                                                                            \
+        int hd = hdiag;                                                                           \
+        hdiag = HIN;                                                                              \
+        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                           \
+            const int d = hd * one + TT[c];                                                       \
+            const int h = max3_s32(d, ER, Fr[c]);                                                 \
+            const int hc = h & cs.MASK;                                                           \
+            ER = addmax_s32(ER, cs.GE, hc * one + cs.GOE);                                        \
+            Fr[c] = addmax_s32(Fr[c], cs.GE, hc * one2 + cs.GOF);                                 \
+            hd = H[c];                                                                            \
+            H[c] = hc;                                                                            \
+        }                                                                                         \
+        OH = H[K - 1];                                                                            \
+        OE = ER;                                                                                  \
+    }
+#define BSA_FLAG1(B, POS)                                                                         \
+    if ((B)&kLastFlag) {                                                                          \
+        const bool valid = (POS) < X;                                                             \
+        if (valid && lane == lane_last) {                                                         \
+            int v = 0;                                                                            \
+            _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = H[c];           \
+            const uint64_t k = out_idx0 + emitted;                                                \
+            if (scores) scores[k] = v >> cs.sh;                                                   \
+            if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                           \
+        }                                                                                         \
+        emitted += valid ? 1u : 0u;                                                               \
+        load_vec<K>(H, rsH + lane);                                                               \
+        load_vec<K>(Fr, rsF + lane);                                                              \
+        hdiag = hdiag0;                                                                           \
+        hb = cs.hb0;                                                                              \
+    }
+
+    for (uint32_t S = 0; S < nd; S += U) {
+        if ((S & 7u) == 0u) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) Fr[c] &= cs.XCLR;
+        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) {
+            nb[u] = ld_code(p + 2 * U + u);   // prefetch the next group's residues
+            any |= b[u];
+        }
+        p += 2 * U;
+        if (!__any_sync(0xffffffffu, any & kLastFlag)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u] & kCodeMask) * ROWB));
+                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u + 1] & kCodeMask) * ROWB));
+                int hin0 = __shfl_up_sync(0xffffffffu, oh0, 1);
+                int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
+                int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
+                int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+                if (lane0) {   // H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101)
+                    hin0 = hb;
+                    er0 = hb + cs.GOE;
+                    hin1 = hb + cs.GEB;
+                    er1 = hin1 + cs.GOE;
+                }
+                hb += 2 * cs.GEB;
+                er0 &= cs.XCLR;   // the streak restarts in every lane
+                er1 &= cs.XCLR;
+                int hd0 = hdiag, hd1 = hin0;
+                hdiag = hin1;
+                int hc1 = 0;
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                    const int d0 = hd0 * one + T0[c];
+                    const int h0 = max3_s32(d0, er0, Fr[c]);
+                    const int hc0 = h0 & cs.MASK;
+                    er0 = addmax_s32(er0, cs.GE, hc0 * one + cs.GOE);
+                    const int f1 = addmax_s32(Fr[c], cs.GE, hc0 * one2 + cs.GOF);
+                    hd0 = H[c];
+                    const int d1 = hd1 * one + T1[c];
+                    const int h1 = max3_s32(d1, er1, f1);
+                    hc1 = h1 & cs.MASK;
+                    er1 = addmax_s32(er1, cs.GE, hc1 * one + cs.GOE);
+                    Fr[c] = addmax_s32(f1, cs.GE, hc1 * one2 + cs.GOF);
+                    hd1 = hc0;
+                    H[c] = hc1;
+                }
+                oh0 = hd1;   // H[r][K-1]
+                oe0 = er0;
+                oh1 = hc1;   // H[r+1][K-1]
+                oe1 = er1;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t pos0 = 2u * (S + u - (uint32_t)lrel);   // wraps below row 0: fails pos < X
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u] & kCodeMask) * ROWB));
+                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u + 1] & kCodeMask) * ROWB));
+                int hin0 = __shfl_up_sync(0xffffffffu, oh0, 1);
+                int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
+                int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
+                int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+                BSA_ROW1(T0, hin0, er0, oh0, oe0)
+                BSA_FLAG1(b[2 * u], pos0)
+                BSA_ROW1(T1, hin1, er1, oh1, oe1)
+                BSA_FLAG1(b[2 * u + 1], pos0 + 1u)
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) b[u] = nb[u];
+    }
+#undef BSA_ROW1
+#undef BSA_FLAG1
+}
+
 __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
                                                     uint32_t hi, uint64_t x) {
     // first index i in [lo, hi] with off[i] >= x
@@ -550,7 +709,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
                 const uint32_t qb = c + 1 == nch ? it.q_end
                                                  : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
                 const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
-                if (g1 > g0)
+                if (g1 <= g0) continue;
+                if constexpr (TAG && !MULTI && TwoRows<K, false>::value)
+                    stream_block_tag2<K, false>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, lane_last, slot_last,
+                                                hdiag0, cs, a.one, a.one2, a.scores, a.nident,
+                                                it.out_base + (qa - it.q_begin));
+                else
                     stream_block<K, false, MULTI, false, false, false, TAG>(
                         a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp, lastp ? lane_last : 31,
                         slot_last, hdiag0, cs, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores, a.nident,
@@ -640,12 +804,17 @@ struct KArgsPair {
 // DP values of template A and template B, both fed by the same query stream, so one
 // VIADDMNMX.S16x2 / VIMNMX.S16x2 / VIADD.16x2 advances two cells.  No tie priorities are needed
 // for the score alone (SURVEY.md 8a note 5): the cell is 5 instructions per TWO cells
-//     t  = max(hdiag + T, e)      VIADDMNMX.S16x2
-//     h  = max(t, f)              VIMNMX.S16x2
-//     hg = h + GO                 VIADD.16x2
-//     e  = max(e + GE, hg)        VIADDMNMX.S16x2
-//     f  = max(f + GE, hg)        VIADDMNMX.S16x2
+//     t  = max(hdiag + T, e)      VIADDMNMX.U16x2
+//     h  = max(t, f)              VIMNMX.U16x2
+//     hg = h + GO                 IMAD (FMA pipe: one 32-bit add does both halves, see below)
+//     e  = max(e + GE, hg)        VIADDMNMX.U16x2
+//     f  = max(f + GE, hg)        VIADDMNMX.U16x2
 // The host only routes template pairs here whose scores provably stay inside 16 bits.
+// Values are stored BIASED by 0x8000 per half (unsigned order == signed order of the true values).
+// The only addition that is not fused into a DPX instruction, hg = h + gap_open, then is a plain
+// 32-bit subtraction of |go| * 0x10001: the low half never borrows from the high half because
+// every biased value in it is >= |go| (host range check), so it runs on the otherwise idle FMA
+// pipe and the ALU pipe carries 4 instead of 5 instructions per two cells.
 struct Item16 {
     uint32_t tA, tB;        // tB == 0xffffffff: single template (high half idle)
     uint32_t q_begin, q_end;
@@ -653,6 +822,8 @@ struct Item16 {
 };
 
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+constexpr uint32_t kBias2 = 0x80008000u;
+__device__ __forceinline__ uint32_t pack2b(int v) { return pack2(v) ^ kBias2; }   // biased halves
 __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
     uint32_t r;
     asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -665,8 +836,8 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
                                                const int lane, const bool first, const bool lastp,
                                                const int lastA, const int slotA, const int lastB,
                                                const int slotB, const uint32_t hdiag0, const uint32_t GE,
-                                               const uint32_t GO, uint2* scratch, int32_t* __restrict__ scores,
-                                               uint64_t outA, uint64_t outB) {
+                                               const uint32_t GO, const int GO32, const int one, uint2* scratch,
+                                               int32_t* __restrict__ scores, uint64_t outA, uint64_t outB) {
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
     constexpr int U = MULTI ? 2 : 4;
     const uint32_t X = (uint32_t)(g1 - g0);
@@ -677,7 +848,7 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
     load_vec<K>(Ha, rsH + lane);
     load_vec<K>(Fr, rsF + lane);
     uint32_t hdiag = hdiag0;
-    uint32_t hb = GO;                 // H[1][0] = gap_open, both halves
+    uint32_t hb = GO ^ kBias2;        // H[1][0] = gap_open, both halves (biased)
     uint32_t oh = 0, oe = 0, emitted = 0;
     const bool border = !MULTI || first;
     const bool lane0 = lane == 0;
@@ -702,11 +873,11 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
         uint32_t hd = hdiag;                                                                      \
         hdiag = hin;                                                                              \
         _Pragma("unroll") for (int c = 0; c < K; ++c) {                                           \
-            const uint32_t t = __viaddmax_s16x2(hd, (uint32_t)T[c], e);                           \
-            const uint32_t h = __vmaxs2(t, (uint32_t)Fr[c]);                                      \
-            const uint32_t hg = add2(h, GO);                                                      \
-            e = __viaddmax_s16x2(e, GE, hg);                                                      \
-            Fr[c] = (int)__viaddmax_s16x2((uint32_t)Fr[c], GE, hg);                               \
+            const uint32_t t = __viaddmax_u16x2(hd, (uint32_t)T[c], e);                           \
+            const uint32_t h = __vmaxu2(t, (uint32_t)Fr[c]);                                      \
+            const uint32_t hg = (uint32_t)((int)h * one + GO32);                                  \
+            e = __viaddmax_u16x2(e, GE, hg);                                                      \
+            Fr[c] = (int)__viaddmax_u16x2((uint32_t)Fr[c], GE, hg);                               \
             hd = (uint32_t)HO[c];                                                                 \
             HN[c] = (int)h;                                                                       \
         }                                                                                         \
@@ -727,19 +898,19 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
                 if (lane == lastA) {                                                              \
                     int v = 0;                                                                    \
                     _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slotA) v = HN[c];      \
-                    scores[outA + emitted] = (int)(short)(v & 0xffff);                            \
+                    scores[outA + emitted] = (v & 0xffff) - 0x8000;                               \
                 }                                                                                 \
                 if (lane == lastB) {                                                              \
                     int v = 0;                                                                    \
                     _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slotB) v = HN[c];      \
-                    scores[outB + emitted] = v >> 16;                                             \
+                    scores[outB + emitted] = (int)((uint32_t)v >> 16) - 0x8000;                   \
                 }                                                                                 \
             }                                                                                     \
             emitted += valid ? 1u : 0u;                                                           \
             load_vec<K>(HN, rsH + lane);                                                          \
             load_vec<K>(Fr, rsF + lane);                                                          \
             hdiag = hdiag0;                                                                       \
-            hb = GO;                                                                              \
+            hb = GO ^ kBias2;                                                                     \
         }                                                                                         \
     }
 
@@ -862,7 +1033,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
             const uint32_t qb = c + 1 == nch ? it.q_end : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
             const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
-            if (g1 > g0)
+            if (g1 <= g0) continue;
+            if constexpr (TAG && TwoRows<K, true>::value)
+                stream_block_tag2<K, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, my_last, my_slot, hdiag0, cs,
+                                           a.one, a.one2, a.scores, a.nident,
+                                           (isB ? it.outB : it.outA) + (qa - it.q_begin));
+            else
                 stream_block<K, false, false, false, false, true, TAG>(
                     a.Q.codes, g0, g1, prof, rsH, rsF, lane, true, true, my_last, my_slot, hdiag0, cs, a.one, nullptr,
                     a.scores, a.nident, (isB ? it.outB : it.outA) + (qa - it.q_begin), nullptr, nullptr, nullptr,
@@ -881,6 +1057,7 @@ struct KArgs16 {
     int32_t* scores;
     uint2* scratch;
     uint32_t scratch_stride;
+    int one;                // runtime 1: keeps hg = h + GO an IMAD
 };
 
 template <int K, bool MULTI>
@@ -894,6 +1071,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
     uint4* rsF = rsH + ROW;
     const int lane = threadIdx.x & 31;
     const uint32_t GE = pack2(a.ge), GO = pack2(a.go);
+    const int GO32 = a.go * 0x10001;   // h + GO32 subtracts |go| from both (biased) halves, no borrow
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -945,8 +1123,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
                 for (int e = 0; e < 4; ++e) {
                     const long long j = (long long)colbase + ln * K + 4 * v + e + 1;
                     const int hv = (int)(a.go + (j - 1) * a.ge);
-                    h[e] = pack2(hv);
-                    f[e] = pack2(hv + a.go);
+                    h[e] = pack2b(hv);
+                    f[e] = pack2b(hv + a.go);
                 }
                 rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
                 rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -959,7 +1137,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
             const int lastB = hasB ? (int)((mB - 1 - colbase) / K) : -1;
             const int slotB = hasB ? (int)((mB - 1 - colbase) % K) : 0;
             const long long jl = (long long)colbase + (long long)lane * K;
-            const uint32_t hdiag0 = jl == 0 ? 0u : pack2((int)(a.go + (jl - 1) * a.ge));
+            const uint32_t hdiag0 = jl == 0 ? kBias2 : pack2b((int)(a.go + (jl - 1) * a.ge));
             for (;;) {
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(&s_chunk, 1u);
@@ -975,7 +1153,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
                 if (g1 > g0)
                     stream_block16<K, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
                                              lastp ? lastA : 31, slotA, lastp ? lastB : 31, slotB, hdiag0, GE, GO,
-                                             MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
+                                             GO32, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
                                              it.outA + (qa - it.q_begin), it.outB + (qa - it.q_begin));
             }
         }

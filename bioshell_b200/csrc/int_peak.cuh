@@ -15,13 +15,13 @@ constexpr int kPeakChains = 8;
 constexpr int kPeakIters = 4096;
 
 template <int WHICH>
-__global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int* sink, unsigned long long* clk) {
+__global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int one2, int* sink, unsigned long long* clk) {
     int a[kPeakChains], b[kPeakChains], c[kPeakChains];
 #pragma unroll
     for (int i = 0; i < kPeakChains; ++i) {
         a[i] = seed + threadIdx.x * 7 + i;
-        b[i] = seed * 3 + i * 5 + 1;
-        c[i] = seed - i;
+        b[i] = seed * 3 + i * 5 + 1 + threadIdx.x;
+        c[i] = seed - i - 3 * threadIdx.x;
     }
     const int ge = seed | 1, go = seed + 3, mask = ~(3 << 12), ph = 2 << 12, pv = 1 << 12;
     unsigned long long c0 = 0, t0 = 0;
@@ -43,6 +43,14 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int* s
                 const int hg = hc * one + go;
                 a[i] = __viaddmax_s32(e, ge, hg);
                 b[i] = __viaddmax_s32(f, ge, hg);
+                c[i] = hc;
+            } else if (WHICH == 7) {
+                // the TAG cell (gotoh_kernels.cuh, cell_row<TAG>): VIMNMX3 + LOP3 + 2 VIADDMNMX (ALU pipe) + 3 IMAD
+                const int d = c[i] * one + ge;
+                const int h = __vimax3_s32(d, a[i], b[i]);
+                const int hc = h & mask;
+                a[i] = __viaddmax_s32(a[i], ge, hc * one + go);
+                b[i] = __viaddmax_s32(b[i], ge, hc * one2 + ph);
                 c[i] = hc;
             } else if (WHICH == 1) {
                 a[i] = __viaddmax_s32(a[i], ge, b[i]);
@@ -75,6 +83,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int* s
 inline int peak_ops_per_iter(int which) {
     switch (which) {
         case 0: return 8;
+        case 7: return 7;
         case 2: return 2;   // VIMNMX3 + the LOP3 that perturbs it
         default: return 1;
     }
@@ -94,13 +103,14 @@ inline cudaError_t measure_int_peak(int which, int sms, cudaStream_t st, double*
     const int blocks = sms * 8;
     auto go = [&](void) {
         switch (which) {
-            case 0: int_peak_kernel<0><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
-            case 1: int_peak_kernel<1><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
-            case 2: int_peak_kernel<2><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
-            case 3: int_peak_kernel<3><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
-            case 4: int_peak_kernel<4><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
-            case 5: int_peak_kernel<5><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
-            default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, 1, sink, clk); break;
+            case 0: int_peak_kernel<0><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 1: int_peak_kernel<1><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 2: int_peak_kernel<2><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 3: int_peak_kernel<3><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 4: int_peak_kernel<4><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 5: int_peak_kernel<5><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 7: int_peak_kernel<7><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
         }
     };
     for (int w = 0; w < 3; ++w) go();
