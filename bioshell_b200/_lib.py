@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbioshell_align.so")
+# BSA_LIB_PATH: A/B experiments against another build of the same library (tools/); the product is the in-tree one
+LIB_PATH = os.environ.get("BSA_LIB_PATH") or os.path.join(_HERE, "libbioshell_align.so")
 
 OK = 0
 ERRORS = {-1: "BAD_ARG", -2: "UNSUPPORTED_GAPS", -3: "RANGE", -4: "CUDA", -5: "OOM", -6: "FORMAT",

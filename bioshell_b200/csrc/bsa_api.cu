@@ -179,11 +179,13 @@ void register_kernels() {
     g_local[32] = gotoh_local_kernel<32>;
     done = true;
 }
-size_t smem_for(int K, int C) { return (size_t)(C + 2) * ((K + 3) / 4) * 32 * sizeof(uint4); }
+// profile + border vectors + the TMA staging area (gotoh_kernels.cuh, smem layout)
+size_t smem_for(int K, int C) { return (size_t)(C + 2) * ((K + 3) / 4) * 32 * sizeof(uint4) + stage_bytes(K, C); }
 
 // largest K whose profile fits the shared-memory budget for an alphabet of C codes
 int k_cap(int C) {
-    size_t vmax = kSmemBudget / ((size_t)(C + 2) * 32 * sizeof(uint4));
+    const size_t stage = stage_bytes(kKMax, C);
+    size_t vmax = (kSmemBudget > stage ? kSmemBudget - stage : 0) / ((size_t)(C + 2) * 32 * sizeof(uint4));
     int kc = (int)std::min<size_t>(kKMax, vmax * 4);
     return kc;
 }
@@ -832,7 +834,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
             const uint64_t m = T.len(t);
             if (cnt == 0 || m == 0 || m > 16ull * kKStream || done16[t - t_begin]) continue;
-            if ((size_t)(C + 2) * ((( (m + 15) / 16) + 3) / 4) * 32 * sizeof(uint4) > kSmemBudget) continue;
+            if (smem_for((int)((m + 15) / 16), C) > kSmemBudget) continue;
             // the kernel sizes the count field for the longer template of a pair: check with the
             // widest field any template of this columns-per-lane class can meet
             const uint64_t m_class = 16ull * ((m + 15) / 16);
@@ -928,20 +930,19 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 ++run_b;
                 continue;
             }
-            if (!fits) {
-                for (uint32_t q = run_b; q < run_e; ++q) fallback.push_back(PairReq{q, t, kbase + q});
-            } else {
-                uint32_t q = run_b;
-                while (q < run_e) {
+            // items of at most xb stream residues over the queries [lo, hi)
+            auto emit_items = [&](uint32_t lo, uint32_t hi, int cshift, bool tag) {
+                uint32_t q = lo;
+                while (q < hi) {
                     const uint64_t lim_off = Q.off[q] + xb;
-                    uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + run_e + 1, lim_off) -
+                    uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + hi + 1, lim_off) -
                                              Q.off.begin()) - 1;
                     q2 = std::max(q2, q + 1);
-                    q2 = std::min(q2, run_e);
+                    q2 = std::min(q2, hi);
                     Item it;
-                    it.t = t; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cs;
+                    it.t = t; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cshift;
                     it.out_base = kbase + q;
-                    Group& grp = groups[group_index(kc.K, kc.multi, fits_tag)];
+                    Group& grp = groups[group_index(kc.K, kc.multi, tag)];
                     grp.items.push_back(it);
                     const uint64_t x = Q.off[q2] - Q.off[q];
                     const double sw = (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
@@ -951,6 +952,15 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                     if (kc.multi) grp.stride = std::max(grp.stride, x + 64);   // boundary column of one item
                     q = q2;
                 }
+            };
+            auto emit_classic = [&](uint32_t lo, uint32_t hi) {
+                if (fits) emit_items(lo, hi, cs, false);
+                else for (uint32_t q = lo; q < hi; ++q) fallback.push_back(PairReq{q, t, kbase + q});
+            };
+            if (fits_tag) {
+                emit_items(run_b, run_e, cs, true);
+            } else {
+                emit_classic(run_b, run_e);
             }
             run_b = run_e;
         }

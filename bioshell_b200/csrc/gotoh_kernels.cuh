@@ -42,6 +42,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// tuning switches (tools/ab_build.sh builds variants of the library for same-box A/B runs)
+#ifndef BSA_TAG2_U
+#define BSA_TAG2_U 2        // double steps per loop iteration of the two-row blocks
+#endif
+#ifndef BSA_RING
+#define BSA_RING 0          // warp-wide prefetch (measured -0.4 % on cfg2: off) of the boundary column in multi-pass kernels
+#endif
+#ifndef BSA_TMA
+#define BSA_TMA 1           // 0: A/B only -- the elected thread copies with plain loads instead of cp.async.bulk
+#endif
+#ifndef BSA_TWO_ROWS
+#define BSA_TWO_ROWS 1      // two-row step where TwoRows<K, HALF> says so
+#endif
+
 namespace bsa {
 
 constexpr int kWarpsPerCta = 8;
@@ -137,17 +151,109 @@ struct KTraits {
     static constexpr int ROW = V * 32;           // uint4 per profile row
 };
 
-// Shared-memory layout (uint4 units): profile rows [C][V][32], then rsH [V][32], rsF [V][32].
+// Shared-memory layout (uint4 units): profile rows [C][V][32], then rsH [V][32], rsF [V][32], then
+// the TMA staging area: the substitution table (C x C int16, rounded up to 16 B) and two template
+// slices of 32 K + 32 bytes each (the 16-byte aligned superset of the columns of one block).
 template <int K>
 __host__ __device__ constexpr size_t smem_bytes(int C) {
     return (size_t)(C + 2) * KTraits<K>::ROW * sizeof(uint4);
 }
+__host__ __device__ constexpr uint32_t subst_stage_bytes(int C) { return ((uint32_t)(C * C * 2) + 15u) & ~15u; }
+__host__ __device__ constexpr uint32_t slice_stage_bytes(int K) { return 32u * (uint32_t)K + 32u; }
+__host__ __device__ constexpr size_t stage_bytes(int K, int C) {
+    return (size_t)subst_stage_bytes(C) + 2u * slice_stage_bytes(K);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA staging.  The substitution table and the template residues a CTA builds its profile from
+// reach shared memory through the bulk-copy engine (cp.async.bulk ... mbarrier::complete_tx,
+// UBLKCP in SASS): one elected thread arms the mbarrier with the byte count and issues the copies,
+// every thread waits on the barrier's phase.  Sources are the 16-byte aligned supersets of the
+// wanted ranges (the packed store has 64/128 bytes of padding around it, the table buffer is
+// over-allocated), sizes are multiples of 16.
+// The barrier's phase bit lives in shared memory (flipped by the elected thread after the
+// barrier that follows each use), so nothing of this occupies a register inside the DP loop.
+struct TmaStage {
+    static __device__ __forceinline__ uint32_t smem_u32(const void* p) {
+        return (uint32_t)__cvta_generic_to_shared(p);
+    }
+    static __device__ __forceinline__ void init(uint64_t* bar) {   // elected thread
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // elected thread: the generic-proxy reads of the staging area that came before (ordered by the
+    // caller's __syncthreads) must be visible to the async proxy before it overwrites the area
+    static __device__ __forceinline__ void arm(uint64_t* bar, uint32_t bytes) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    }
+    static __device__ __forceinline__ void copy(uint64_t* bar, void* dst_smem, const void* src, uint32_t bytes) {
+#if !BSA_TMA
+        for (uint32_t i = 0; i < bytes; i += 16)
+            *reinterpret_cast<uint4*>(reinterpret_cast<char*>(dst_smem) + i) =
+                *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(src) + i);
+        asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        return;
+#endif
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    }
+    static __device__ __forceinline__ void wait(uint64_t* bar, uint32_t phase) {   // every thread
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        } while (!done);
+    }
+};
+
+// Kernel preamble: set up the mbarrier and bring the substitution table in (once per CTA; it does
+// not change between items).  BSA_TMA_PTRS carves the staging area behind the profile.
+#define BSA_TMA_PTRS(KK, CC)                                                                      \
+    uint8_t* stage = reinterpret_cast<uint8_t*>(rsF + KTraits<KK>::ROW);                          \
+    const int16_t* s_subst = reinterpret_cast<const int16_t*>(stage);                             \
+    uint8_t* s_tcA = stage + subst_stage_bytes(CC);                                               \
+    uint8_t* s_tcB = s_tcA + slice_stage_bytes(KK);                                               \
+    (void)s_subst; (void)s_tcB;
+#define BSA_TMA_PREAMBLE(KK, CC, SUBST)                                                           \
+    __shared__ uint64_t s_mbar;                                                                   \
+    __shared__ uint32_t s_phase;                                                                  \
+    if (threadIdx.x == 0) {                                                                       \
+        TmaStage::init(&s_mbar);                                                                  \
+        TmaStage::arm(&s_mbar, subst_stage_bytes(CC));                                            \
+        TmaStage::copy(&s_mbar, rsF + KTraits<KK>::ROW, SUBST, subst_stage_bytes(CC));            \
+        s_phase = 1;                                                                              \
+    }                                                                                             \
+    __syncthreads();                                                                              \
+    TmaStage::wait(&s_mbar, 0);
+// after the __syncthreads that follows a use: the elected thread flips the phase for the next one
+#define BSA_TMA_FLIP() if (threadIdx.x == 0) s_phase ^= 1u;
+
+// Stage the columns [colbase, colbase + ncols) of the template that starts at `tc` into `dst`;
+// returns the pointer p with p[col] == tc[col] for those columns.  Called by the elected thread
+// between arm() and wait(); `bytes_out` is what it asked the copy engine for.
+__device__ __forceinline__ uint32_t slice_bytes(const uint8_t* tc, uint32_t colbase, uint32_t ncols) {
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(tc + colbase) & 15u);
+    return (head + ncols + 15u) & ~15u;
+}
+__device__ __forceinline__ const uint8_t* slice_view(const uint8_t* dst, const uint8_t* tc, uint32_t colbase) {
+    const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(tc + colbase) & 15u);
+    return dst + head - colbase;
+}
+__device__ __forceinline__ const uint8_t* slice_src(const uint8_t* tc, uint32_t colbase) {
+    return reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(tc + colbase) & ~(uintptr_t)15u);
+}
 
 // Build the profile of template columns [colbase, colbase + 32K) and the per-lane
 // top-border reset vectors.  All threads of the CTA participate.
+// `subst` and `tc` point into the TMA staging area (tc[col] valid for this block's columns).
 template <int K>
 __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rsF,
-                                              const uint8_t* __restrict__ tc, uint32_t m,
+                                              const int16_t* subst, const uint8_t* tc, uint32_t m,
                                               uint32_t colbase, const KArgs& a, const Consts& cs) {
     constexpr int ROW = KTraits<K>::ROW;
     const int C = a.C;
@@ -166,7 +272,7 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
             int val = cs.T_PAD;
             if (c < K && col < m) {
                 const int tcode = tc[col] & kCodeMask;
-                val = (int)a.subst[code * C + tcode] * S + P3 +
+                val = (int)subst[code * C + tcode] * S + P3 +
                       ((cs.cs > 0 && tcode == code && !gap) ? 1 : 0);   // no count field when cs == 0
             }
             o[e] = val;
@@ -327,17 +433,34 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 #pragma unroll
     for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
     uint2 sc_next = make_uint2(0u, 0u);
+    // Boundary column of the block to the left (multi-pass templates).  Without WAVE it is complete
+    // before this pass starts, so the warp fetches it 32 entries at a time, one per lane and a whole
+    // batch ahead (an L2 round trip is longer than a step), and lane 0 takes entry S by shuffle.
+    constexpr bool RING = MULTI && !WAVE && BSA_RING;
+    uint2 ring_cur = make_uint2(0u, 0u), ring_nxt = make_uint2(0u, 0u);
+    if (RING && !first) {
+        if ((uint32_t)lane < X) ring_cur = scratch[lane];
+        if (32u + (uint32_t)lane < X) ring_nxt = scratch[32 + lane];
+    }
     if (WAVE && !first && X > 0) {
         if (lane0) while ((avail = ld_acquire_u32(prog_in)) < 1u) {}
         avail = __shfl_sync(0xffffffffu, avail, 0);
     }
-    if (MULTI && !first && lane0 && X > 0) sc_next = scratch[0];
+    if (MULTI && !RING && !first && lane0 && X > 0) sc_next = scratch[0];
 
     // one step; HO = previous row, HN = this row
 #define BSA_STEP_CORE(HO, HN, B, S)                                                               \
         load_vec<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB));       \
         int hin = __shfl_up_sync(0xffffffffu, oh, 1);                                             \
         int er = __shfl_up_sync(0xffffffffu, oe, 1);                                              \
+        if (RING && !first) {                                                                     \
+            sc_next.x = __shfl_sync(0xffffffffu, ring_cur.x, (S)&31u);                            \
+            sc_next.y = __shfl_sync(0xffffffffu, ring_cur.y, (S)&31u);                            \
+            if (((S)&31u) == 31u) {                                                               \
+                ring_cur = ring_nxt;                                                              \
+                if ((S) + 33u + (uint32_t)lane < X) ring_nxt = scratch[(S) + 33u + lane];         \
+            }                                                                                     \
+        }                                                                                         \
         if (lane0) {                                                                              \
             if (border) { /* H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101) */ \
                 hin = LOCAL ? 0 : hb;            /* local: H[i][0] = E[i][1] = 0 (local.rs:116) */ \
@@ -348,7 +471,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             }                                                                                     \
         }                                                                                         \
         if (TAG) er &= cs.XCLR;   /* the streak restarts in every lane */                         \
-        if (MULTI && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];                  \
+        if (MULTI && !RING && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];         \
         hb += cs.GEB;                                                                             \
         const int hd = hdiag;                                                                     \
         hdiag = hin;                                                                              \
@@ -457,7 +580,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 // one-row step is as fast or faster.
 template <int K, bool HALF>
 struct TwoRows {
-    static constexpr bool value = HALF ? (K >= 8 && K != 11 && K != 12 && K != 19) : (K >= 13 && K <= 19);
+    static constexpr bool value = BSA_TWO_ROWS && (HALF ? (K >= 8 && K != 11 && K != 12 && K != 19) : (K >= 13 && K <= 19));
 };
 
 template <int K, bool HALF>
@@ -468,7 +591,7 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
                                                   int32_t* __restrict__ scores, uint32_t* __restrict__ nident,
                                                   uint64_t out_idx0) {
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
-    constexpr int U = K <= 10 ? 2 : 1;          // double steps per loop iteration
+    constexpr int U = BSA_TAG2_U;  // double steps per loop iteration (an even count lets H[] return to its registers)
     static_assert(8 % U == 0, "the F streak is cleared every 8 double steps");
     const uint32_t X = (uint32_t)(g1 - g0);
     const int span = HALF ? 15 : lane_last;
@@ -660,6 +783,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
     uint4* rsH = smem + (size_t)a.C * ROW;
     uint4* rsF = rsH + ROW;
     const int lane = threadIdx.x & 31;
+    BSA_TMA_PREAMBLE(K, a.C, a.subst)
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -687,10 +811,20 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
 
         for (uint32_t pass = 0; pass < npass; ++pass) {
             const uint32_t colbase = pass * 32 * K;
-            __syncthreads();   // previous profile / chunk counter are no longer in use
-            if (threadIdx.x == 0) s_chunk = 0;
-            build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
+            __syncthreads();   // previous profile / chunk counter / staged slice are no longer in use
+            {
+                BSA_TMA_PTRS(K, a.C)
+                if (threadIdx.x == 0) {
+                    s_chunk = 0;
+                    const uint32_t nb = slice_bytes(tc, colbase, min(m - colbase, 32u * K));
+                    TmaStage::arm(&s_mbar, nb);
+                    TmaStage::copy(&s_mbar, s_tcA, slice_src(tc, colbase), nb);
+                }
+                TmaStage::wait(&s_mbar, s_phase);
+                build_profile<K>(prof, rsH, rsF, s_subst, slice_view(s_tcA, tc, colbase), m, colbase, a, cs);
+            }
             __syncthreads();
+            BSA_TMA_FLIP()
             const bool lastp = (pass + 1 == npass);
             const int lane_last = (int)((m - 1 - colbase) / K);
             const int slot_last = (int)((m - 1 - colbase) % K);
@@ -738,6 +872,7 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
     uint4* rsF = rsH + ROW;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    BSA_TMA_PREAMBLE(K, a.C, a.subst)
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -754,8 +889,18 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
         for (uint32_t pass = 0; pass < npass; ++pass) {
             const uint32_t colbase = pass * 32 * K;
             __syncthreads();
-            build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
+            {
+                BSA_TMA_PTRS(K, a.C)
+                if (threadIdx.x == 0) {
+                    const uint32_t nb = slice_bytes(tc, colbase, min(m - colbase, 32u * K));
+                    TmaStage::arm(&s_mbar, nb);
+                    TmaStage::copy(&s_mbar, s_tcA, slice_src(tc, colbase), nb);
+                }
+                TmaStage::wait(&s_mbar, s_phase);
+                build_profile<K>(prof, rsH, rsF, s_subst, slice_view(s_tcA, tc, colbase), m, colbase, a, cs);
+            }
             __syncthreads();
+            BSA_TMA_FLIP()
             const bool lastp = (pass + 1 == npass);
             const int lane_last = (int)((m - 1 - colbase) / K);
             const int slot_last = (int)((m - 1 - colbase) % K);
@@ -858,17 +1003,31 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
 #pragma unroll
     for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
     uint2 sc_next = make_uint2(0u, 0u);
-    if (MULTI && !first && lane0 && X > 0) sc_next = scratch[0];
+    uint2 ring_cur = make_uint2(0u, 0u), ring_nxt = make_uint2(0u, 0u);   // see stream_block
+    constexpr bool RING = MULTI && BSA_RING;
+    if (RING && !first) {
+        if ((uint32_t)lane < X) ring_cur = scratch[lane];
+        if (32u + (uint32_t)lane < X) ring_nxt = scratch[32 + lane];
+    }
+    if (MULTI && !RING && !first && lane0 && X > 0) sc_next = scratch[0];
 
 #define BSA_STEP16_CORE(HO, HN, B, S)                                                             \
         load_vec<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB));       \
         uint32_t hin = __shfl_up_sync(0xffffffffu, oh, 1);                                        \
         uint32_t e = __shfl_up_sync(0xffffffffu, oe, 1);                                          \
+        if (RING && !first) {                                                                     \
+            sc_next.x = __shfl_sync(0xffffffffu, ring_cur.x, (S)&31u);                            \
+            sc_next.y = __shfl_sync(0xffffffffu, ring_cur.y, (S)&31u);                            \
+            if (((S)&31u) == 31u) {                                                               \
+                ring_cur = ring_nxt;                                                              \
+                if ((S) + 33u + (uint32_t)lane < X) ring_nxt = scratch[(S) + 33u + lane];         \
+            }                                                                                     \
+        }                                                                                         \
         if (lane0) {                                                                              \
             if (border) { hin = hb; e = add2(hb, GO); }                                           \
             else { hin = sc_next.x; e = sc_next.y; }                                              \
         }                                                                                         \
-        if (MULTI && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];                  \
+        if (MULTI && !RING && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];         \
         hb = add2(hb, GE);                                                                        \
         uint32_t hd = hdiag;                                                                      \
         hdiag = hin;                                                                              \
@@ -943,6 +1102,146 @@ __device__ __forceinline__ void stream_block16(const uint8_t* __restrict__ codes
 #undef BSA_STEP16_CORE
 }
 
+// Two rows per step for the 16-bit score-only lanes (one column block): same idea as
+// stream_block_tag2 -- lanes skewed by two stream positions, cell (r+1, c) right after cell (r, c),
+// H in place.  The 16-bit cell is a chain of four dependent instructions per two cells and only
+// 2 ALU-pipe instructions per cell, so with one row in flight the warp mostly waits on itself.
+template <int K>
+__device__ __forceinline__ void stream_block16_2r(const uint8_t* __restrict__ codes, uint64_t g0, uint64_t g1,
+                                                  const uint4* prof, const uint4* rsH, const uint4* rsF,
+                                                  const int lane, const int lastA, const int slotA,
+                                                  const int lastB, const int slotB, const uint32_t hdiag0,
+                                                  const uint32_t GE, const uint32_t GO, const int GO32,
+                                                  const int one, int32_t* __restrict__ scores, uint64_t outA,
+                                                  uint64_t outB) {
+    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int U = BSA_TAG2_U;
+    const uint32_t X = (uint32_t)(g1 - g0);
+    const int span = lastA > lastB ? lastA : lastB;
+    const uint32_t nd = ((X + 1u) / 2u + (uint32_t)span + (U - 1)) / U * U;
+    const bool lane0 = lane == 0;
+
+    int H[K], Fr[K], T0[K], T1[K];
+    load_vec<K>(H, rsH + lane);
+    load_vec<K>(Fr, rsF + lane);
+    uint32_t hdiag = hdiag0, hb = GO ^ kBias2;
+    uint32_t oh0 = 0, oe0 = 0, oh1 = 0, oe1 = 0, emitted = 0;
+    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
+    const uint8_t* p = codes + g0 - 2 * lane;
+    uint32_t b[2 * U], nb[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) b[u] = ld_code(p + u);
+
+#define BSA_ROW16(TT, HIN, E, OH, OE)                                                             \
+    {                                                                                             \
+        if (lane0) { HIN = hb; E = add2(hb, GO); }                                                \
+        hb = add2(hb, GE);                                                                        \
+        uint32_t hd = hdiag;                                                                      \
+        hdiag = HIN;                                                                              \
+        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                           \
+            const uint32_t t = __viaddmax_u16x2(hd, (uint32_t)TT[c], E);                          \
+            const uint32_t h = __vmaxu2(t, (uint32_t)Fr[c]);                                      \
+            const uint32_t hg = (uint32_t)((int)h * one + GO32);                                  \
+            E = __viaddmax_u16x2(E, GE, hg);                                                      \
+            Fr[c] = (int)__viaddmax_u16x2((uint32_t)Fr[c], GE, hg);                               \
+            hd = (uint32_t)H[c];                                                                  \
+            H[c] = (int)h;                                                                        \
+        }                                                                                         \
+        OH = (uint32_t)H[K - 1];                                                                  \
+        OE = E;                                                                                   \
+    }
+#define BSA_FLAG16(B, POS)                                                                        \
+    if ((B)&kLastFlag) {                                                                          \
+        const bool valid = (POS) < X;                                                             \
+        if (valid && scores) {                                                                    \
+            if (lane == lastA) {                                                                  \
+                int v = 0;                                                                        \
+                _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slotA) v = H[c];           \
+                scores[outA + emitted] = (v & 0xffff) - 0x8000;                                   \
+            }                                                                                     \
+            if (lane == lastB) {                                                                  \
+                int v = 0;                                                                        \
+                _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slotB) v = H[c];           \
+                scores[outB + emitted] = (int)((uint32_t)v >> 16) - 0x8000;                       \
+            }                                                                                     \
+        }                                                                                         \
+        emitted += valid ? 1u : 0u;                                                               \
+        load_vec<K>(H, rsH + lane);                                                               \
+        load_vec<K>(Fr, rsF + lane);                                                              \
+        hdiag = hdiag0;                                                                           \
+        hb = GO ^ kBias2;                                                                         \
+    }
+
+    for (uint32_t S = 0; S < nd; S += U) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) {
+            nb[u] = ld_code(p + 2 * U + u);
+            any |= b[u];
+        }
+        p += 2 * U;
+        if (!__any_sync(0xffffffffu, any & kLastFlag)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u] & kCodeMask) * ROWB));
+                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u + 1] & kCodeMask) * ROWB));
+                uint32_t hin0 = __shfl_up_sync(0xffffffffu, oh0, 1);
+                uint32_t e0 = __shfl_up_sync(0xffffffffu, oe0, 1);
+                uint32_t hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
+                uint32_t e1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+                if (lane0) {
+                    hin0 = hb;
+                    e0 = add2(hb, GO);
+                    hin1 = add2(hb, GE);
+                    e1 = add2(hin1, GO);
+                }
+                hb = add2(add2(hb, GE), GE);
+                uint32_t hd0 = hdiag, hd1 = hin0, h1 = 0;
+                hdiag = hin1;
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                    const uint32_t t0 = __viaddmax_u16x2(hd0, (uint32_t)T0[c], e0);
+                    const uint32_t h0 = __vmaxu2(t0, (uint32_t)Fr[c]);
+                    const uint32_t hg0 = (uint32_t)((int)h0 * one + GO32);
+                    e0 = __viaddmax_u16x2(e0, GE, hg0);
+                    const uint32_t f1 = __viaddmax_u16x2((uint32_t)Fr[c], GE, hg0);
+                    hd0 = (uint32_t)H[c];
+                    const uint32_t t1 = __viaddmax_u16x2(hd1, (uint32_t)T1[c], e1);
+                    h1 = __vmaxu2(t1, f1);
+                    const uint32_t hg1 = (uint32_t)((int)h1 * one + GO32);
+                    e1 = __viaddmax_u16x2(e1, GE, hg1);
+                    Fr[c] = (int)__viaddmax_u16x2(f1, GE, hg1);
+                    hd1 = h0;
+                    H[c] = (int)h1;
+                }
+                oh0 = hd1;
+                oe0 = e0;
+                oh1 = h1;
+                oe1 = e1;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t pos0 = 2u * (S + u - (uint32_t)lane);
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u] & kCodeMask) * ROWB));
+                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u + 1] & kCodeMask) * ROWB));
+                uint32_t hin0 = __shfl_up_sync(0xffffffffu, oh0, 1);
+                uint32_t e0 = __shfl_up_sync(0xffffffffu, oe0, 1);
+                uint32_t hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
+                uint32_t e1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+                BSA_ROW16(T0, hin0, e0, oh0, oe0)
+                BSA_FLAG16(b[2 * u], pos0)
+                BSA_ROW16(T1, hin1, e1, oh1, oe1)
+                BSA_FLAG16(b[2 * u + 1], pos0 + 1u)
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) b[u] = nb[u];
+    }
+#undef BSA_ROW16
+#undef BSA_FLAG16
+}
+
 template <int K, bool TAG = false>
 __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kernel(const KArgsPair a) {
     extern __shared__ uint4 smem[];
@@ -955,6 +1254,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
     const int lane = threadIdx.x & 31;
     const int lrel = lane & 15;
     const bool isB = lane >= 16;
+    BSA_TMA_PREAMBLE(K, a.C, a.subst)
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -982,12 +1282,23 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const uint32_t nch = nbig + nsmall;
 
         __syncthreads();
-        if (threadIdx.x == 0) s_chunk = 0;
+        BSA_TMA_PTRS(K, a.C)
+        if (threadIdx.x == 0) {
+            s_chunk = 0;
+            const uint32_t nbA = slice_bytes(a.T.codes + a0, 0, mA);
+            const uint32_t nbB = hasB ? slice_bytes(a.T.codes + b0, 0, mB) : 0u;
+            TmaStage::arm(&s_mbar, nbA + nbB);
+            TmaStage::copy(&s_mbar, s_tcA, slice_src(a.T.codes + a0, 0), nbA);
+            if (hasB) TmaStage::copy(&s_mbar, s_tcB, slice_src(a.T.codes + b0, 0), nbB);
+        }
+        TmaStage::wait(&s_mbar, s_phase);
+        const uint8_t* vA = slice_view(s_tcA, a.T.codes + a0, 0);
+        const uint8_t* vB = slice_view(s_tcB, a.T.codes + b0, 0);
         // profile: lanes 0-15 hold the columns of template A, lanes 16-31 those of template B
         for (int idx = threadIdx.x; idx < a.C * ROW; idx += blockDim.x) {
             const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
             const bool b = ln >= 16;
-            const uint8_t* tc = a.T.codes + (b ? b0 : a0);
+            const uint8_t* tc = b ? vB : vA;
             const uint32_t m = b ? mB : mA;
             const bool gap = a.isgap[code] != 0;
             int o[4];
@@ -998,7 +1309,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
                 int val = cs.T_PAD;
                 if (c < K && col < m) {
                     const int tcode = tc[col] & kCodeMask;
-                    val = (int)a.subst[code * a.C + tcode] * S + P3 + ((tcode == code && !gap) ? 1 : 0);
+                    val = (int)s_subst[code * a.C + tcode] * S + P3 + ((tcode == code && !gap) ? 1 : 0);
                 }
                 o[e] = val;
             }
@@ -1017,6 +1328,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
         }
         __syncthreads();
+        BSA_TMA_FLIP()
         const uint32_t mine = isB ? mB : mA;
         // a lane emits only for its own template; an absent template B never matches a lane
         const int my_last = (isB && !hasB) ? -1 : (int)((mine - 1) / K) + (isB ? 16 : 0);
@@ -1060,8 +1372,13 @@ struct KArgs16 {
     int one;                // runtime 1: keeps hg = h + GO an IMAD
 };
 
+// the two-row step keeps two chains in flight per warp, so the single-block kernels trade the third
+// resident CTA for a spill-free 128-register budget from K = 10 on
 template <int K, bool MULTI>
-__global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_kernel(const KArgs16 a) {
+struct MinBlocks16 { static constexpr int value = (!MULTI && K >= 10) ? 2 : MinBlocks<K>::value; };
+
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_score16_kernel(const KArgs16 a) {
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_item;
     __shared__ uint32_t s_chunk;
@@ -1072,6 +1389,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
     const int lane = threadIdx.x & 31;
     const uint32_t GE = pack2(a.ge), GO = pack2(a.go);
     const int GO32 = a.go * 0x10001;   // h + GO32 subtracts |go| from both (biased) halves, no borrow
+    BSA_TMA_PREAMBLE(K, a.C, a.subst)
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -1101,7 +1419,21 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
         for (uint32_t pass = 0; pass < npass; ++pass) {
             const uint32_t colbase = pass * 32 * K;
             __syncthreads();
-            if (threadIdx.x == 0) s_chunk = 0;
+            BSA_TMA_PTRS(K, a.C)
+            if (threadIdx.x == 0) {
+                s_chunk = 0;
+                // a template that ends before this block contributes no columns (zero-length copy is skipped)
+                const uint32_t ncA = mA > colbase ? min(mA - colbase, 32u * K) : 0u;
+                const uint32_t ncB = mB > colbase ? min(mB - colbase, 32u * K) : 0u;
+                const uint32_t nbA = ncA ? slice_bytes(tcA, colbase, ncA) : 0u;
+                const uint32_t nbB = ncB ? slice_bytes(tcB, colbase, ncB) : 0u;
+                TmaStage::arm(&s_mbar, nbA + nbB);
+                if (ncA) TmaStage::copy(&s_mbar, s_tcA, slice_src(tcA, colbase), nbA);
+                if (ncB) TmaStage::copy(&s_mbar, s_tcB, slice_src(tcB, colbase), nbB);
+            }
+            TmaStage::wait(&s_mbar, s_phase);
+            const uint8_t* vA = slice_view(s_tcA, tcA, colbase);
+            const uint8_t* vB = slice_view(s_tcB, tcB, colbase);
             // packed profile: low half template A, high half template B
             for (int idx = threadIdx.x; idx < a.C * ROW; idx += blockDim.x) {
                 const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
@@ -1110,8 +1442,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
                 for (int e = 0; e < 4; ++e) {
                     const int c = 4 * v + e;
                     const uint32_t col = colbase + ln * K + c;
-                    const int sa = (c < K && col < mA) ? (int)a.subst[code * a.C + (tcA[col] & kCodeMask)] : 0;
-                    const int sb = (c < K && col < mB) ? (int)a.subst[code * a.C + (tcB[col] & kCodeMask)] : 0;
+                    const int sa = (c < K && col < mA) ? (int)s_subst[code * a.C + (vA[col] & kCodeMask)] : 0;
+                    const int sb = (c < K && col < mB) ? (int)s_subst[code * a.C + (vB[col] & kCodeMask)] : 0;
                     o[e] = ((uint32_t)sa & 0xffffu) | ((uint32_t)sb << 16);
                 }
                 prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1130,6 +1462,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
                 rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
             }
             __syncthreads();
+            BSA_TMA_FLIP()
             const bool lastp = (pass + 1 == npass);
             // a template that ends in an earlier block never emits from this kernel: the host only
             // pairs templates with the same number of blocks
@@ -1150,7 +1483,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_score16_k
                 const uint32_t qb = c + 1 == nch ? it.q_end
                                                  : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
                 const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
-                if (g1 > g0)
+                if (g1 <= g0) continue;
+                if constexpr (!MULTI)
+                    stream_block16_2r<K>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, lastA, slotA, lastB, slotB, hdiag0,
+                                         GE, GO, GO32, a.one, a.scores, it.outA + (qa - it.q_begin),
+                                         it.outB + (qa - it.q_begin));
+                else
                     stream_block16<K, MULTI>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
                                              lastp ? lastA : 31, slotA, lastp ? lastB : 31, slotB, hdiag0, GE, GO,
                                              GO32, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
@@ -1360,6 +1698,7 @@ __global__ void __launch_bounds__(kThreads) gotoh_local_kernel(const KArgs a, Lo
     uint4* rsF = rsH + ROW;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    BSA_TMA_PREAMBLE(K, a.C, a.subst)
 
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
@@ -1376,8 +1715,18 @@ __global__ void __launch_bounds__(kThreads) gotoh_local_kernel(const KArgs a, Lo
         for (uint32_t pass = 0; pass < npass; ++pass) {
             const uint32_t colbase = pass * 32 * K;
             __syncthreads();
-            build_profile<K>(prof, rsH, rsF, tc, m, colbase, a, cs);
+            {
+                BSA_TMA_PTRS(K, a.C)
+                if (threadIdx.x == 0) {
+                    const uint32_t nb = slice_bytes(tc, colbase, min(m - colbase, 32u * K));
+                    TmaStage::arm(&s_mbar, nb);
+                    TmaStage::copy(&s_mbar, s_tcA, slice_src(tc, colbase), nb);
+                }
+                TmaStage::wait(&s_mbar, s_phase);
+                build_profile<K>(prof, rsH, rsF, s_subst, slice_view(s_tcA, tc, colbase), m, colbase, a, cs);
+            }
             __syncthreads();
+            BSA_TMA_FLIP()
             const bool lastp = (pass + 1 == npass);
             for (uint32_t pi = it.q_begin + warp; pi < it.q_end; pi += kWarpsPerCta) {
                 const PairRec pr = a.pairs[pi];
