@@ -303,13 +303,15 @@ def main():
             "roofline": {"bound": "alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
                          "frac": achieved / peak_ops,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the hot kernel
-                         # family (gotoh_pair_kernel<16>, 54.1 ms, 1.2e11 cells) from the ncu --set full
-                         # capture in profiles/r1_ncu_summary_final.md; algorithmic HBM bytes of that
+                         # family (gotoh_pair_kernel<20, TAG>, 36.96 ms, 1.16e11 cells) from the ncu --set full
+                         # capture in profiles/r1_ncu_summary_tag.md; algorithmic HBM bytes of that
                          # launch are ~8 B/pair of results + the 2.9 MB sequence store
-                         "traffic": 3046656,
+                         "traffic": 3426816,
                          "note": "integer/DPX issue roofline per GPU: cells/s x %.1f lane-instructions per cell vs the same "
-                                 "instruction mix measured live by bsa_measure_int_peak (of measured; SM clock %.0f MHz "
-                                 "during that probe). HBM is not the bound: algorithmic traffic is 8 B/pair." % (ops_per_cell, peak_mhz),
+                                 "instruction mix (all-vs-all: the TAG cell, VIMNMX3 + LOP3 + 2 VIADDMNMX + 3 IMAD; one-vs-many: "
+                                 "ALU-pipe instructions only against the VIADDMNMX.S16x2 rate) in independent chains, measured "
+                                 "live by bsa_measure_int_peak (of measured; SM clock %.0f MHz during that probe). HBM is "
+                                 "not the bound: algorithmic traffic is 8 B/pair." % (ops_per_cell, peak_mhz),
                          "hbm_algorithmic_gbs": (pairs * 8 / world) / (ms_per_step / 1e3) / 1e9},
         }
         if not args.no_cpu_baseline and world == 1 and not ovm:
