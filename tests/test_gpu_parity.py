@@ -288,3 +288,56 @@ def test_score_only_long_sequences_leave_16bit_lanes(ctx, oracle_matrices):
     ref = c_oracle.align_all_pairs(S, S, M[0], M[1], -10, -1, False, n_threads=8, with_backtrace=False)
     assert np.array_equal(s, ref["score"])
     assert ctx.stats()["items"] > 0
+
+
+def _long_gap_set(seed):
+    """Pairs whose optimal paths hold gaps far longer than the TAG cell's 5-bit streak field and
+    the 16-row clearing period: very short against long sequences (both orientations), long
+    sequences with a long insertion, runs of one residue (many equal-score ties), plus filler."""
+    rng = random.Random(seed)
+    core = bytes(rng.choice(AA) for _ in range(40))
+    seqs = [bytes(rng.choice(AA) for _ in range(n)) for n in (3, 7, 12, 25, 33, 64, 65)]
+    seqs += [bytes(rng.choice(AA) for _ in range(n)) for n in (300, 317, 500, 640, 641, 900)]
+    for ins in (35, 70, 130, 260):           # same ends, a long insertion in the middle
+        seqs.append(core[:20] + bytes(rng.choice(AA) for _ in range(ins)) + core[20:])
+    seqs.append(core)
+    seqs += [b"A" * 50, b"A" * 333, b"AW" * 100, b"W" * 45 + b"A" * 200 + b"W" * 45, b"W" * 90]
+    seqs += [bytes(rng.choice(AA) for _ in range(rng.randint(1, 700))) for _ in range(20)]
+    rng.shuffle(seqs)
+    return seqs
+
+
+@pytest.mark.parametrize("matrix,go,ge", [("BLOSUM62", -10, -1), ("BLOSUM62", -11, -1), ("BLOSUM62", -4, -4),
+                                          ("PAM250", -2, 0)])
+def test_long_gaps_through_every_cell_variant(ctx, oracle_matrices, monkeypatch, matrix, go, ge):
+    """The TAG cell (streak field cleared at lane boundaries and every 16 rows), its two-row step,
+    the paired short-template kernel and the classic cell must all give the oracle's scores and
+    identities when gaps run over hundreds of cells; BSA_NO_TAG / BSA_NO_PAIR select the classic
+    cell and the one-template kernels for the same inputs."""
+    seqs = _long_gap_set(17)
+    res, off = bs.pack(seqs)
+    ref = oracle_triangle(res, off, oracle_matrices[matrix], go, ge)
+    ctx.set_scoring(matrix, go, ge)
+    ctx.load_sequences(0, res, off)
+    for env in ({}, {"BSA_NO_TAG": "1"}, {"BSA_NO_PAIR": "1"}, {"BSA_NO_TAG": "1", "BSA_NO_PAIR": "1"}):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            scores, nid = ctx.all_vs_all(0)
+        bad = np.nonzero((scores != ref["score"]) | (nid != ref["n_identical"]))[0]
+        assert len(bad) == 0, (env, bad[:5], scores[bad[:5]], ref["score"][bad[:5]])
+        assert ctx.stats()["fallback_pairs"] == 0
+
+
+def test_score_only_lanes_long_gaps_and_large_gap_open(ctx, oracle_matrices):
+    """16-bit biased lanes (two-row step, `h + go` as one 32-bit IMAD): long gaps, and a gap-open
+    large enough that a borrow between the halves would show if a biased value fell below |go|."""
+    seqs = _long_gap_set(23)
+    res, off = bs.pack(seqs)
+    for matrix, go, ge in (("BLOSUM62", -10, -1), ("BLOSUM62", -700, -1), ("PAM30", -30, -5)):
+        ref = oracle_triangle(res, off, oracle_matrices[matrix], go, ge)
+        ctx.set_scoring(matrix, go, ge)
+        ctx.load_sequences(0, res, off)
+        scores, _ = ctx.align_all_pairs(0, 0, np.arange(len(seqs), dtype=np.uint32), want_identical=False)
+        bad = np.nonzero(scores != ref["score"])[0]
+        assert len(bad) == 0, (matrix, go, ge, bad[:5], scores[bad[:5]], ref["score"][bad[:5]])
