@@ -181,7 +181,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the alignment has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner (and any debug output) to
+        # stdout unless told otherwise
+        if os.environ.get("NCCL_DEBUG"):
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

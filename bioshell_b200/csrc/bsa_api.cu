@@ -443,11 +443,12 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         ta.n_pairs = (uint32_t)recs.size();
         ta.dirs = ctx->dirs.as<uint32_t>();
         ta.isgap = ctx->d_isgap.as<uint8_t>();
+        ta.ncodes = (uint32_t)std::max(ctx->ncodes, 1);
         ta.path = path_buf ? ctx->path.as<uint8_t>() : nullptr;
         ta.path_start = ctx->pstart.as<uint32_t>();
         ta.nident = d_nid;
         ta.status = ctx->status.as<uint32_t>();
-        const uint32_t tb_blocks = (ta.n_pairs + kTraceThreads - 1) / kTraceThreads;
+        const uint32_t tb_blocks = (ta.n_pairs + kTraceThreads / 32 - 1) / (kTraceThreads / 32);   // one warp per pair
         if (local) traceback_local_kernel<<<tb_blocks, kTraceThreads, 0, st>>>(ta, d_lout);
         else traceback_kernel<<<tb_blocks, kTraceThreads, 0, st>>>(ta);
         CK(cudaGetLastError());

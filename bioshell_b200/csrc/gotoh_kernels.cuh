@@ -1590,77 +1590,116 @@ struct TraceArgs {
     uint32_t n_pairs;
     const uint32_t* dirs;
     const uint8_t* isgap;
+    uint32_t ncodes;        // entries of isgap
     uint8_t* path;          // may be null (identity only)
     uint32_t* path_start;   // per pair (by position in `pairs`): first byte of the path in its slot
     uint32_t* nident;       // indexed by PairRec::out, may be null
     uint32_t* status;       // set to 1 if an invalid direction is met
 };
 
-// The walk mostly moves diagonally, i.e. one step (a new 128-byte line) back per glyph, and
-// every load depends on the previous one.  DirWindow keeps, per thread, the direction words of the
-// current (pass, lane, word) column for the last kTraceWin steps: a refill issues kTraceWin
-// independent loads at once, so the DRAM/L2 latency is paid once per kTraceWin glyphs.
-constexpr int kTraceWin = 16;
-constexpr int kTraceThreads = 64;
+// One WARP walks one pair; all 32 lanes run the same (uniform) walk, lane 0 writes.  The walk mostly
+// moves diagonally, i.e. one step (a new 128-byte line) back per glyph, and every load depends on
+// the previous one: the warp therefore keeps the direction words of the current (pass, lane, word)
+// column for the last 32 steps, one per lane -- a refill is ONE warp-wide load of 32 independent
+// lines, and a lookup is a shuffle.  (With one thread per pair, the threads of a warp diverged on
+// every refill and every state change and all waited for the slowest.)
+constexpr int kTraceWin = 32;
+constexpr int kTraceThreads = 256;          // 8 pairs per CTA
 
 struct DirWindow {
-    uint32_t key = 0xffffffffu, top = 0;
-    __device__ __forceinline__ uint32_t get(uint32_t* win, const uint32_t* __restrict__ dirs, size_t plane,
-                                            uint32_t W, uint32_t pass, uint32_t step, uint32_t lane, uint32_t w) {
+    uint32_t key = 0xffffffffu, top = 0, v = 0;
+    __device__ __forceinline__ uint32_t get(const uint32_t* __restrict__ dirs, size_t plane, uint32_t W,
+                                            uint32_t pass, uint32_t step, uint32_t lane, uint32_t w,
+                                            uint32_t me) {
         const uint32_t k = (pass * 32u + lane) * 4u + w;
-        if (k != key || step > top || step + kTraceWin <= top) {
+        if (k != key || step > top || step + kTraceWin <= top) {      // warp-uniform
             key = k;
             top = step;
             const uint32_t* base = dirs + pass * plane + (size_t)lane * W + w;
-            uint32_t v[kTraceWin];
-#pragma unroll
-            for (int d = 0; d < kTraceWin; ++d)
-                v[d] = (uint32_t)d <= step ? base[(size_t)(step - d) * 32 * W] : 0u;
-#pragma unroll
-            for (int d = 0; d < kTraceWin; ++d) win[d] = v[d];
+            v = me <= step ? base[(size_t)(step - me) * 32 * W] : 0u;
         }
-        return win[top - step];
+        return __shfl_sync(0xffffffffu, v, top - step);
+    }
+};
+
+// Position of DP column j in the direction planes -- (pass, lane, slot) -- kept incrementally: the
+// walk only ever moves one column to the left, so the two divisions by the runtime K are paid once.
+struct ColCursor {
+    uint32_t K, pass, lane, c;
+    __device__ __forceinline__ void init(uint32_t K_, uint32_t j) {   // j >= 1
+        K = K_;
+        const uint32_t col = j - 1, BK = 32 * K;
+        pass = col / BK;
+        const uint32_t lc = col - pass * BK;
+        lane = lc / K;
+        c = lc - lane * K;
+    }
+    __device__ __forceinline__ void left() {
+        if (c > 0) { --c; return; }
+        c = K - 1;
+        if (lane > 0) { --lane; return; }
+        lane = 31;
+        --pass;            // wraps at column 0; the walk stops there (j == 0)
+    }
+    __device__ __forceinline__ uint32_t word() const { return c >> 3; }
+    __device__ __forceinline__ uint32_t shift() const {
+        const uint32_t w = c >> 3;
+        const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
+        return 4 * (cnt - 1 - (c & 7));
     }
 };
 
 __global__ void traceback_kernel(const TraceArgs a) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t me = threadIdx.x & 31u;
+    const bool writer = me == 0;
     if (p >= a.n_pairs) return;
     const PairRec pr = a.pairs[p];
     const uint8_t* qc = a.Q.codes + a.Q.off[pr.q];
     const uint8_t* tc = a.T.codes + a.T.off[pr.t];
     const uint32_t n = (uint32_t)(a.Q.off[pr.q + 1] - a.Q.off[pr.q]);
     const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - a.T.off[pr.t]);
-    const uint32_t K = pr.k, W = (K + 7) / 8, BK = 32 * K;
+    const uint32_t K = pr.k, W = (K + 7) / 8;
     const size_t plane = (size_t)(n + 32) * 32 * W;
     const uint32_t* dirs = a.dirs + pr.dir_off;
-    uint8_t* out = a.path ? a.path + pr.path_off : nullptr;
+    uint8_t* out = (a.path && writer) ? a.path + pr.path_off : nullptr;
     uint32_t pos = n + m, i = n, j = m, nid = 0;
     int st = 0;
-    __shared__ uint32_t s_win[kTraceThreads][kTraceWin + 1];
     DirWindow dw;
+    // '-' / '_' codes as bit masks (msa.rs:264), so the identity test is register-only
+    unsigned long long gap_lo = 0ull, gap_hi = 0ull;
+    for (uint32_t code = 0; code < a.ncodes; ++code)
+        if (a.isgap[code]) {
+            if (code < 64) gap_lo |= 1ull << code; else gap_hi |= 1ull << (code - 64);
+        }
+    ColCursor cur;
+    if (j > 0) cur.init(K, j);
+    // the residues of a diagonal step are only needed for the count: they are consumed one
+    // diagonal step later, so their loads never stall the walk
+    uint32_t px = 0xffu, py = 0xfeu;
+#define BSA_COUNT_PENDING() \
+    nid += (px == py && !((((px & 64u) ? gap_hi : gap_lo) >> (px & 63u)) & 1ull)) ? 1u : 0u;
     while (i > 0 && j > 0) {
-        const uint32_t col = j - 1, pass = col / BK, lc = col - pass * BK;
-        const uint32_t lane = lc / K, c = lc - lane * K;
-        const uint32_t step = (i - 1) + lane, w = c >> 3;
-        const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
-        const uint32_t sh = 4 * (cnt - 1 - (c & 7));
-        const uint32_t nib = (dw.get(s_win[threadIdx.x], dirs, plane, W, pass, step, lane, w) >> sh) & 15u;
+        const uint32_t step = (i - 1) + cur.lane;
+        const uint32_t nib = (dw.get(dirs, plane, W, cur.pass, step, cur.lane, cur.word(), me) >> cur.shift()) & 15u;
         if (st == 0) {
             const uint32_t hd = nib & 3u;
             if (hd == 3u) {
                 --pos;
                 if (out) out[pos] = '*';
-                const uint32_t x = qc[i - 1] & kCodeMask, y = tc[j - 1] & kCodeMask;
-                nid += (x == y && !a.isgap[x]) ? 1u : 0u;
+                BSA_COUNT_PENDING()
+                px = qc[i - 1] & kCodeMask;
+                py = tc[j - 1] & kCodeMask;
                 --i; --j;
+                cur.left();
             } else if (hd == 2u) st = 1;
             else if (hd == 1u) st = 2;
-            else { *a.status = 1u; break; }
+            else { if (writer) *a.status = 1u; break; }
         } else if (st == 1) {
             --pos;
             if (out) out[pos] = '-';
             --j;
+            cur.left();
             st = (nib & 8u) ? 1 : 0;
         } else {
             --pos;
@@ -1669,11 +1708,15 @@ __global__ void traceback_kernel(const TraceArgs a) {
             st = (nib & 4u) ? 2 : 0;
         }
     }
+    BSA_COUNT_PENDING()
+#undef BSA_COUNT_PENDING
     // borders: row 0 is all E-extensions, column 0 all F-extensions (global.rs:81-88,96-97)
     while (j > 0) { --pos; if (out) out[pos] = '-'; --j; }
     while (i > 0) { --pos; if (out) out[pos] = '|'; --i; }
-    a.path_start[p] = pos;
-    if (a.nident) a.nident[pr.out] = nid;
+    if (writer) {
+        a.path_start[p] = pos;
+        if (a.nident) a.nident[pr.out] = nid;
+    }
 }
 
 // Local alignment (LocalAlignment::align, bioshell-seq/src/alignment/local.rs:83-207): the
@@ -1766,36 +1809,36 @@ __global__ void __launch_bounds__(kThreads) gotoh_local_kernel(const KArgs a, Lo
 
 // LocalAlignment::backtrace (local.rs:213-273): from the best cell, state H, until a STOP
 __global__ void traceback_local_kernel(const TraceArgs a, LocalOut* __restrict__ lout) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t me = threadIdx.x & 31u;
+    const bool writer = me == 0;
     if (p >= a.n_pairs) return;
     const PairRec pr = a.pairs[p];
     const uint32_t n = (uint32_t)(a.Q.off[pr.q + 1] - a.Q.off[pr.q]);
     const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - a.T.off[pr.t]);
-    const uint32_t K = pr.k, W = (K + 7) / 8, BK = 32 * K;
+    const uint32_t K = pr.k, W = (K + 7) / 8;
     const size_t plane = (size_t)(n + 32) * 32 * W;
     const uint32_t* dirs = a.dirs + pr.dir_off;
-    uint8_t* out = a.path ? a.path + pr.path_off : nullptr;
+    uint8_t* out = (a.path && writer) ? a.path + pr.path_off : nullptr;
     LocalOut lo = lout[pr.out];
     uint32_t pos = n + m, i = lo.end_q, j = lo.end_t;
     int st = 0;
-    __shared__ uint32_t s_win[kTraceThreads][kTraceWin + 1];
     DirWindow dw;
+    ColCursor cur;
+    if (j > 0) cur.init(K, j);
     while (i > 0 && j > 0) {
-        const uint32_t col = j - 1, pass = col / BK, lc = col - pass * BK;
-        const uint32_t lane = lc / K, c = lc - lane * K;
-        const uint32_t step = (i - 1) + lane, w = c >> 3;
-        const uint32_t cnt = (K - 8 * w) < 8 ? (K - 8 * w) : 8;
-        const uint32_t sh = 4 * (cnt - 1 - (c & 7));
-        const uint32_t nib = (dw.get(s_win[threadIdx.x], dirs, plane, W, pass, step, lane, w) >> sh) & 15u;
+        const uint32_t step = (i - 1) + cur.lane;
+        const uint32_t nib = (dw.get(dirs, plane, W, cur.pass, step, cur.lane, cur.word(), me) >> cur.shift()) & 15u;
         if (st == 0) {
             const uint32_t hd = nib & 3u;
             if (hd == 0u) break;                                   // arrows == 0: STOP
-            if (hd == 3u) { --pos; if (out) out[pos] = '*'; --i; --j; }
+            if (hd == 3u) { --pos; if (out) out[pos] = '*'; --i; --j; cur.left(); }
             else if (hd == 2u) st = 1;
             else st = 2;
         } else if (st == 1) {
             --pos; if (out) out[pos] = '-';
             --j;
+            cur.left();
             st = (nib & 8u) ? 1 : 0;
         } else {
             --pos; if (out) out[pos] = '|';
@@ -1803,10 +1846,12 @@ __global__ void traceback_local_kernel(const TraceArgs a, LocalOut* __restrict__
             st = (nib & 4u) ? 2 : 0;
         }
     }
-    a.path_start[p] = pos;
-    lo.start_q = i;
-    lo.start_t = j;
-    lout[pr.out] = lo;
+    if (writer) {
+        a.path_start[p] = pos;
+        lo.start_q = i;
+        lo.start_t = j;
+        lout[pr.out] = lo;
+    }
 }
 
 // ---- sequence-store construction (K0) ----
