@@ -22,7 +22,8 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 torch.cuda.set_device(local)
 if world > 1:
-    os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 res, off = synth.config("cfg3", n=n)
 lens = np.diff(off.astype(np.int64))
