@@ -1454,11 +1454,54 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     ctx->stats.launches++;
     uint32_t merge_grid = std::max(1u, std::min(24u, (n + 255u) / 256u));
     if (const char* e = getenv("BSA_HC_MERGE_GRID")) merge_grid = (uint32_t)std::max(1, atoi(e));   // debugging aid
-    for (uint32_t step = 0; step + 1 < n; ++step) {
-        hclust_argmin_kernel<<<grid, 256, 0, st>>>(hs);
-        hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, grid, done_counter);
-        ctx->stats.launches += 2;
+    // Every merge is the same two launches with the same arguments (the state lives on the device),
+    // and late merges are launch-latency bound: replay them from CUDA graphs of kHcGraphMerges
+    // merges.  The scan grid shrinks with the live matrix (one warp per ~2 rows, the full grid
+    // from 4096 rows up), in power-of-two levels so that a handful of graphs covers the whole run.
+    constexpr uint32_t kHcGraphMerges = 64;
+    constexpr int kHcLevels = 7;
+    auto level_for = [&](uint32_t order) {
+        const uint64_t want = std::max<uint64_t>(16, (uint64_t)order * grid / 4096);
+        int l = 0;
+        while (l + 1 < kHcLevels && (grid >> (l + 1)) >= want) ++l;
+        return l;
+    };
+    const bool use_graph = !getenv("BSA_HC_NO_GRAPH");
+    cudaGraphExec_t execs[kHcLevels] = {nullptr};
+    cudaError_t ge = cudaSuccess;
+    const uint32_t n_merges = n - 1;
+    uint32_t step = 0;
+    while (step < n_merges && ge == cudaSuccess) {
+        const uint32_t order = n - step;                 // rows alive before this merge
+        const int l = level_for(order);
+        const uint32_t g = std::max(1u, grid >> l);
+        if (use_graph && step + kHcGraphMerges <= n_merges) {
+            if (!execs[l]) {
+                cudaGraph_t graph = nullptr;
+                ge = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+                if (ge != cudaSuccess) break;
+                for (uint32_t k = 0; k < kHcGraphMerges; ++k) {
+                    hclust_argmin_kernel<<<g, 256, 0, st>>>(hs);
+                    hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, g, done_counter);
+                }
+                ge = cudaStreamEndCapture(st, &graph);
+                if (ge != cudaSuccess) break;
+                ge = cudaGraphInstantiate(&execs[l], graph, 0);
+                cudaGraphDestroy(graph);
+                if (ge != cudaSuccess) break;
+            }
+            ge = cudaGraphLaunch(execs[l], st);
+            ctx->stats.launches += 2 * kHcGraphMerges;
+            step += kHcGraphMerges;
+        } else {
+            hclust_argmin_kernel<<<g, 256, 0, st>>>(hs);
+            hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, g, done_counter);
+            ctx->stats.launches += 2;
+            ++step;
+        }
     }
+    for (int l = 0; l < kHcLevels; ++l) if (execs[l]) cudaGraphExecDestroy(execs[l]);
+    if (ge != cudaSuccess) return fail_cuda(ctx, ge, "hclust graph replay");
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_end, st));
     uint32_t fin[2] = {0, 0};

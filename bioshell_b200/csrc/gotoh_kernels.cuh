@@ -52,6 +52,12 @@
 #ifndef BSA_TMA
 #define BSA_TMA 1           // 0: A/B only -- the elected thread copies with plain loads instead of cp.async.bulk
 #endif
+#ifndef BSA_MB3_MAXK
+#define BSA_MB3_MAXK 12     // largest K that still runs three CTAs per SM (80 registers per thread)
+#endif
+#ifndef BSA_CHUNK_BIG
+#define BSA_CHUNK_BIG 4096  // stream residues per big chunk
+#endif
 #ifndef BSA_TWO_ROWS
 #define BSA_TWO_ROWS 1      // two-row step where TwoRows<K, HALF> says so
 #endif
@@ -580,7 +586,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 // one-row step is as fast or faster.
 template <int K, bool HALF>
 struct TwoRows {
-    static constexpr bool value = BSA_TWO_ROWS && (HALF ? (K >= 8 && K != 11 && K != 12 && K != 19) : (K >= 13 && K <= 19));
+    static constexpr bool value = BSA_TWO_ROWS && (HALF ? (K >= 8 && K != 19 && (K > BSA_MB3_MAXK || (K != 11 && K != 12)))
+                                                        : (K > BSA_MB3_MAXK && K <= 19));
 };
 
 template <int K, bool HALF>
@@ -768,9 +775,9 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool l
 // not progress at the same rate -- the issue arbiter is not fair -- so a static split
 // would leave the fast warps waiting at the item's closing barrier).
 template <int K>
-struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= 12 ? 3 : 2); };
+struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= BSA_MB3_MAXK ? 3 : 2); };
 
-constexpr uint32_t kChunkBig = 4096;    // stream residues per chunk (pipeline fill is 31 steps)
+constexpr uint32_t kChunkBig = BSA_CHUNK_BIG;    // stream residues per chunk (pipeline fill is 31 steps)
 constexpr uint32_t kChunkSmall = 640;
 
 template <int K, bool MULTI, bool TAG = false>
