@@ -9,3 +9,5 @@ from .scoring import SubstitutionMatrix, SubstitutionMatrixList, ncbi_text  # no
 from .sequence import Sequence, count_identical, len_ungapped, pack, ungapped_lengths  # noqa: F401
 from . import clustering  # noqa: F401,E402
 from . import bucket_clustering  # noqa: F401,E402
+from .fasta import FastaIterator, load_sequences  # noqa: F401,E402
+from .sequence_id import LabelStyle, SeqId, SeqIdList, parse_sequence_id, sequence_label  # noqa: F401,E402

@@ -217,7 +217,9 @@ def aligned_sequences(path, query, template, gap_symbol="-"):
 # alignment_statistics.rs / alignment_reporter.rs / cluster_sequences.rs
 # ---------------------------------------------------------------------------
 class AlignmentStatistics:
-    """alignment_statistics.rs:28-81 (labels are the raw descriptions here)."""
+    """alignment_statistics.rs:28-81.  `label_style` is a `sequence_id.LabelStyle`
+    (sequence_label.rs:33-63); None keeps the raw descriptions (the batched path never builds
+    labels per pair -- the reference runs ~17 regex scans per reported pair here)."""
 
     def __init__(self, query_header, template_header, n_identical, query_length, template_length):
         self.query_header, self.template_header = query_header, template_header
@@ -225,8 +227,11 @@ class AlignmentStatistics:
 
     @classmethod
     def from_sequences(cls, aligned_query, aligned_template, label_style=None):
-        return cls(aligned_query.description(), aligned_template.description(),
-                   count_identical(aligned_query, aligned_template),
+        qh, th = aligned_query.description(), aligned_template.description()
+        if label_style is not None:
+            from .sequence_id import sequence_label
+            qh, th = sequence_label(qh, label_style), sequence_label(th, label_style)
+        return cls(qh, th, count_identical(aligned_query, aligned_template),
                    len_ungapped(aligned_query), len_ungapped(aligned_template))
 
     @classmethod

@@ -21,6 +21,7 @@ import numpy as np
 
 from . import _lib
 from .alignment import SequenceIdentityMatrix, align_all_vs_all, default_context
+from .sequence_id import LabelStyle, sequence_label
 
 sys.setrecursionlimit(max(sys.getrecursionlimit(), 1000000))
 
@@ -341,11 +342,11 @@ def cluster_sequences(sequences, linkage, gap_open=-10, gap_extend=-2, identity_
     out["order"] = seq_order
     if distance_matrix and write_files:                                                  # :232-248
         with open(distance_matrix, "w") as fh:
+            style = LabelStyle.FullId(True, name_width)                                  # :231
+            labels = {i: sequence_label(sequences[i].description(), style) for i in seq_order}
             for k, i in enumerate(seq_order):
-                qn = sequences[i].description()[:name_width]
                 for l, j in enumerate(seq_order):
-                    fh.write("%s\t%s\t%6.3f\t%d\t%d\n" % (qn, sequences[j].description()[:name_width],
-                                                           ident[i, j], k, l))
+                    fh.write("%s\t%s\t%6.3f\t%d\t%d\n" % (labels[i], labels[j], ident[i, j], k, l))
                 fh.write("\n")
     if fasta and write_files:                                                            # :251-256
         with open(fasta, "w") as fh:

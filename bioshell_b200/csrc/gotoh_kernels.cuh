@@ -58,6 +58,9 @@
 #ifndef BSA_CHUNK_BIG
 #define BSA_CHUNK_BIG 4096  // stream residues per big chunk
 #endif
+#ifndef BSA_FLAG_SPLIT
+#define BSA_FLAG_SPLIT 0     // two-row blocks: a flagged double step whose flags all sit on its second row keeps the interleaved form
+#endif
 #ifndef BSA_TWO_ROWS
 #define BSA_TWO_ROWS 1      // two-row step where TwoRows<K, HALF> says so
 #endif
@@ -655,6 +658,43 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
         hb = cs.hb0;                                                                              \
     }
 
+    // two rows interleaved, in place (needs: no lane ends a sequence on the FIRST of the two rows)
+#define BSA_PAIR2()                                                                               \
+    {                                                                                             \
+        if (lane0) {                                                                              \
+            hin0 = hb;                                                                            \
+            er0 = hb + cs.GOE;                                                                    \
+            hin1 = hb + cs.GEB;                                                                   \
+            er1 = hin1 + cs.GOE;                                                                  \
+        }                                                                                         \
+        hb += 2 * cs.GEB;                                                                         \
+        er0 &= cs.XCLR;                                                                           \
+        er1 &= cs.XCLR;                                                                           \
+        int hd0 = hdiag, hd1 = hin0;                                                              \
+        hdiag = hin1;                                                                             \
+        int hc1 = 0;                                                                              \
+_Pragma("unroll")                                                                                 \
+        for (int c = 0; c < K; ++c) {                                                             \
+            const int d0 = hd0 * one + T0[c];                                                     \
+            const int h0 = max3_s32(d0, er0, Fr[c]);                                              \
+            const int hc0 = h0 & cs.MASK;                                                         \
+            er0 = addmax_s32(er0, cs.GE, hc0 * one + cs.GOE);                                     \
+            const int f1 = addmax_s32(Fr[c], cs.GE, hc0 * one2 + cs.GOF);                         \
+            hd0 = H[c];                                                                           \
+            const int d1 = hd1 * one + T1[c];                                                     \
+            const int h1 = max3_s32(d1, er1, f1);                                                 \
+            hc1 = h1 & cs.MASK;                                                                   \
+            er1 = addmax_s32(er1, cs.GE, hc1 * one + cs.GOE);                                     \
+            Fr[c] = addmax_s32(f1, cs.GE, hc1 * one2 + cs.GOF);                                   \
+            hd1 = hc0;                                                                            \
+            H[c] = hc1;                                                                           \
+        }                                                                                         \
+        oh0 = hd1;                                                                                \
+        oe0 = er0;                                                                                \
+        oh1 = hc1;                                                                                \
+        oe1 = er1;                                                                                \
+    }
+
     for (uint32_t S = 0; S < nd; S += U) {
         if ((S & 7u) == 0u) {
 #pragma unroll
@@ -676,38 +716,7 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
                 int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-                if (lane0) {   // H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101)
-                    hin0 = hb;
-                    er0 = hb + cs.GOE;
-                    hin1 = hb + cs.GEB;
-                    er1 = hin1 + cs.GOE;
-                }
-                hb += 2 * cs.GEB;
-                er0 &= cs.XCLR;   // the streak restarts in every lane
-                er1 &= cs.XCLR;
-                int hd0 = hdiag, hd1 = hin0;
-                hdiag = hin1;
-                int hc1 = 0;
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                    const int d0 = hd0 * one + T0[c];
-                    const int h0 = max3_s32(d0, er0, Fr[c]);
-                    const int hc0 = h0 & cs.MASK;
-                    er0 = addmax_s32(er0, cs.GE, hc0 * one + cs.GOE);
-                    const int f1 = addmax_s32(Fr[c], cs.GE, hc0 * one2 + cs.GOF);
-                    hd0 = H[c];
-                    const int d1 = hd1 * one + T1[c];
-                    const int h1 = max3_s32(d1, er1, f1);
-                    hc1 = h1 & cs.MASK;
-                    er1 = addmax_s32(er1, cs.GE, hc1 * one + cs.GOE);
-                    Fr[c] = addmax_s32(f1, cs.GE, hc1 * one2 + cs.GOF);
-                    hd1 = hc0;
-                    H[c] = hc1;
-                }
-                oh0 = hd1;   // H[r][K-1]
-                oe0 = er0;
-                oh1 = hc1;   // H[r+1][K-1]
-                oe1 = er1;
+                BSA_PAIR2()
             }
         } else {
 #pragma unroll
@@ -719,10 +728,16 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
                 int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-                BSA_ROW1(T0, hin0, er0, oh0, oe0)
-                BSA_FLAG1(b[2 * u], pos0)
-                BSA_ROW1(T1, hin1, er1, oh1, oe1)
-                BSA_FLAG1(b[2 * u + 1], pos0 + 1u)
+                if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, b[2 * u] & kLastFlag)) {
+                    // flags only on the second row: the interleaved step stays valid, reset afterwards
+                    BSA_PAIR2()
+                    BSA_FLAG1(b[2 * u + 1], pos0 + 1u)
+                } else {
+                    BSA_ROW1(T0, hin0, er0, oh0, oe0)
+                    BSA_FLAG1(b[2 * u], pos0)
+                    BSA_ROW1(T1, hin1, er1, oh1, oe1)
+                    BSA_FLAG1(b[2 * u + 1], pos0 + 1u)
+                }
             }
         }
 #pragma unroll
@@ -730,6 +745,7 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
     }
 #undef BSA_ROW1
 #undef BSA_FLAG1
+#undef BSA_PAIR2
 }
 
 __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
@@ -1179,6 +1195,40 @@ __device__ __forceinline__ void stream_block16_2r(const uint8_t* __restrict__ co
         hb = GO ^ kBias2;                                                                         \
     }
 
+    // two rows interleaved (needs: no lane ends a sequence on the FIRST of the two rows)
+#define BSA_PAIR16()                                                                              \
+    {                                                                                             \
+        if (lane0) {                                                                              \
+            hin0 = hb;                                                                            \
+            e0 = add2(hb, GO);                                                                    \
+            hin1 = add2(hb, GE);                                                                  \
+            e1 = add2(hin1, GO);                                                                  \
+        }                                                                                         \
+        hb = add2(add2(hb, GE), GE);                                                              \
+        uint32_t hd0 = hdiag, hd1 = hin0, h1 = 0;                                                 \
+        hdiag = hin1;                                                                             \
+_Pragma("unroll")                                                                                 \
+        for (int c = 0; c < K; ++c) {                                                             \
+            const uint32_t t0 = __viaddmax_u16x2(hd0, (uint32_t)T0[c], e0);                       \
+            const uint32_t h0 = __vmaxu2(t0, (uint32_t)Fr[c]);                                    \
+            const uint32_t hg0 = (uint32_t)((int)h0 * one + GO32);                                \
+            e0 = __viaddmax_u16x2(e0, GE, hg0);                                                   \
+            const uint32_t f1 = __viaddmax_u16x2((uint32_t)Fr[c], GE, hg0);                       \
+            hd0 = (uint32_t)H[c];                                                                 \
+            const uint32_t t1 = __viaddmax_u16x2(hd1, (uint32_t)T1[c], e1);                       \
+            h1 = __vmaxu2(t1, f1);                                                                \
+            const uint32_t hg1 = (uint32_t)((int)h1 * one + GO32);                                \
+            e1 = __viaddmax_u16x2(e1, GE, hg1);                                                   \
+            Fr[c] = (int)__viaddmax_u16x2(f1, GE, hg1);                                           \
+            hd1 = h0;                                                                             \
+            H[c] = (int)h1;                                                                       \
+        }                                                                                         \
+        oh0 = hd1;                                                                                \
+        oe0 = e0;                                                                                 \
+        oh1 = h1;                                                                                 \
+        oe1 = e1;                                                                                 \
+    }
+
     for (uint32_t S = 0; S < nd; S += U) {
         uint32_t any = 0;
 #pragma unroll
@@ -1196,35 +1246,7 @@ __device__ __forceinline__ void stream_block16_2r(const uint8_t* __restrict__ co
                 uint32_t e0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 uint32_t hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 uint32_t e1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-                if (lane0) {
-                    hin0 = hb;
-                    e0 = add2(hb, GO);
-                    hin1 = add2(hb, GE);
-                    e1 = add2(hin1, GO);
-                }
-                hb = add2(add2(hb, GE), GE);
-                uint32_t hd0 = hdiag, hd1 = hin0, h1 = 0;
-                hdiag = hin1;
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                    const uint32_t t0 = __viaddmax_u16x2(hd0, (uint32_t)T0[c], e0);
-                    const uint32_t h0 = __vmaxu2(t0, (uint32_t)Fr[c]);
-                    const uint32_t hg0 = (uint32_t)((int)h0 * one + GO32);
-                    e0 = __viaddmax_u16x2(e0, GE, hg0);
-                    const uint32_t f1 = __viaddmax_u16x2((uint32_t)Fr[c], GE, hg0);
-                    hd0 = (uint32_t)H[c];
-                    const uint32_t t1 = __viaddmax_u16x2(hd1, (uint32_t)T1[c], e1);
-                    h1 = __vmaxu2(t1, f1);
-                    const uint32_t hg1 = (uint32_t)((int)h1 * one + GO32);
-                    e1 = __viaddmax_u16x2(e1, GE, hg1);
-                    Fr[c] = (int)__viaddmax_u16x2(f1, GE, hg1);
-                    hd1 = h0;
-                    H[c] = (int)h1;
-                }
-                oh0 = hd1;
-                oe0 = e0;
-                oh1 = h1;
-                oe1 = e1;
+                BSA_PAIR16()
             }
         } else {
 #pragma unroll
@@ -1236,10 +1258,15 @@ __device__ __forceinline__ void stream_block16_2r(const uint8_t* __restrict__ co
                 uint32_t e0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 uint32_t hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 uint32_t e1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-                BSA_ROW16(T0, hin0, e0, oh0, oe0)
-                BSA_FLAG16(b[2 * u], pos0)
-                BSA_ROW16(T1, hin1, e1, oh1, oe1)
-                BSA_FLAG16(b[2 * u + 1], pos0 + 1u)
+                if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, b[2 * u] & kLastFlag)) {
+                    BSA_PAIR16()
+                    BSA_FLAG16(b[2 * u + 1], pos0 + 1u)
+                } else {
+                    BSA_ROW16(T0, hin0, e0, oh0, oe0)
+                    BSA_FLAG16(b[2 * u], pos0)
+                    BSA_ROW16(T1, hin1, e1, oh1, oe1)
+                    BSA_FLAG16(b[2 * u + 1], pos0 + 1u)
+                }
             }
         }
 #pragma unroll
@@ -1247,6 +1274,7 @@ __device__ __forceinline__ void stream_block16_2r(const uint8_t* __restrict__ co
     }
 #undef BSA_ROW16
 #undef BSA_FLAG16
+#undef BSA_PAIR16
 }
 
 template <int K, bool TAG = false>

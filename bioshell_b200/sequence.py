@@ -13,7 +13,15 @@ class Sequence:
 
     def __init__(self, description, seq):
         self._description = description
-        self._seq = seq.encode() if isinstance(seq, str) else bytes(seq)
+        # `Sequence::new` / `from_str` drop blanks from a string (sequence.rs:34-39,69-71,190-192);
+        # bytes are taken as they are, like `from_attrs` (sequence.rs:54-56)
+        if isinstance(seq, str):
+            seq = seq.replace(" ", "")
+            try:
+                seq = seq.encode("latin-1")
+            except UnicodeEncodeError:                       # `c as u8` keeps the low byte
+                seq = bytes(ord(c) & 0xFF for c in seq)
+        self._seq = bytes(seq)
 
     @classmethod
     def from_str(cls, description, seq):
