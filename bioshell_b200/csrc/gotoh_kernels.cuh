@@ -49,6 +49,15 @@
 #ifndef BSA_RING
 #define BSA_RING 0          // warp-wide prefetch (measured -0.4 % on cfg2: off) of the boundary column in multi-pass kernels
 #endif
+#ifndef BSA_WAVE_RING
+#define BSA_WAVE_RING 1     // K3: warp-wide batches of 32 boundary entries instead of lane 0's per-step load (one L2 round trip per row); 0: A/B only
+#endif
+#ifndef BSA_WAVE_POLL
+#define BSA_WAVE_POLL 0     // K3: poll the hand-off counter with relaxed loads (+ nanosleep) and acquire once, instead of an acquire (= L1 invalidate) per poll
+#endif
+#ifndef BSA_WAVE_PD
+#define BSA_WAVE_PD 1       // K3: residue groups fetched ahead (1 = the next group only)
+#endif
 #ifndef BSA_TMA
 #define BSA_TMA 1           // 0: A/B only -- the elected thread copies with plain loads instead of cp.async.bulk
 #endif
@@ -389,6 +398,23 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Wait until *p >= need.  Every ld.acquire.gpu is followed by an L1 invalidate (CCTL.IVALL) that
+// also evicts the co-resident warps' lines, and a waiting block polls thousands of times: with
+// BSA_WAVE_POLL the polls are relaxed loads with a short sleep in between and ONE acquire follows.
+__device__ __forceinline__ uint32_t wait_progress(const uint32_t* p, uint32_t need) {
+    uint32_t v;
+#if BSA_WAVE_POLL
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= need) break;
+        __nanosleep(64);
+    }
+    v = ld_acquire_u32(p);
+#else
+    while ((v = ld_acquire_u32(p)) < need) {}
+#endif
+    return v;
+}
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -438,22 +464,42 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     LaneBest lbest{0, 0u, 0u};
 
     const uint8_t* p = codes + g0 - lrel;   // lane's position at step 0 (may sit in the padding)
-    uint32_t b[U], nb[U];
+    // residues are fetched PD groups ahead (WAVE: a row is short next to an L2 round trip)
+    constexpr int PD = WAVE ? BSA_WAVE_PD : 1;
+    uint32_t b[U], nb[PD][U];
 #pragma unroll
     for (int u = 0; u < U; ++u) b[u] = ld_code(p + u);
+#pragma unroll
+    for (int g = 0; g + 1 < PD; ++g) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) nb[g][u] = ld_code(p + (g + 1) * U + u);
+    }
     uint2 sc_next = make_uint2(0u, 0u);
     // Boundary column of the block to the left (multi-pass templates).  Without WAVE it is complete
     // before this pass starts, so the warp fetches it 32 entries at a time, one per lane and a whole
     // batch ahead (an L2 round trip is longer than a step), and lane 0 takes entry S by shuffle.
-    constexpr bool RING = MULTI && !WAVE && BSA_RING;
+    // With WAVE the left block is still running: it publishes its boundary in batches of 32 entries
+    // (prog_out), so this block takes a batch with ONE warp-wide load (L1 bypassed) as soon as it
+    // is published, half a batch before its first entry is needed (kWavePf), and runs 56+ rows
+    // behind its left neighbour.  (Lane 0 loading entry S+1 at step S made every row wait for an
+    // L2 round trip: ~830 cycles per row on B200.)
+    constexpr bool WRING = MULTI && WAVE && BSA_WAVE_RING;
+    constexpr bool RING = MULTI && ((!WAVE && BSA_RING) || WRING);
+    constexpr uint32_t kWavePf = 8;   // step inside a batch at which the next batch is fetched (even)
     uint2 ring_cur = make_uint2(0u, 0u), ring_nxt = make_uint2(0u, 0u);
-    if (RING && !first) {
-        if ((uint32_t)lane < X) ring_cur = scratch[lane];
-        if (32u + (uint32_t)lane < X) ring_nxt = scratch[32 + lane];
-    }
     if (WAVE && !first && X > 0) {
-        if (lane0) while ((avail = ld_acquire_u32(prog_in)) < 1u) {}
+        const uint32_t need0 = WRING ? (X < 32u ? X : 32u) : 1u;
+        if (lane0) avail = wait_progress(prog_in, need0);
         avail = __shfl_sync(0xffffffffu, avail, 0);
+        __syncwarp();
+    }
+    if (RING && !first) {
+        if (WRING) {
+            if ((uint32_t)lane < X) ring_cur = __ldcg(scratch + lane);
+        } else {
+            if ((uint32_t)lane < X) ring_cur = scratch[lane];
+            if (32u + (uint32_t)lane < X) ring_nxt = scratch[32 + lane];
+        }
     }
     if (MULTI && !RING && !first && lane0 && X > 0) sc_next = scratch[0];
 
@@ -467,7 +513,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             sc_next.y = __shfl_sync(0xffffffffu, ring_cur.y, (S)&31u);                            \
             if (((S)&31u) == 31u) {                                                               \
                 ring_cur = ring_nxt;                                                              \
-                if ((S) + 33u + (uint32_t)lane < X) ring_nxt = scratch[(S) + 33u + lane];         \
+                if (!WRING && (S) + 33u + (uint32_t)lane < X) ring_nxt = scratch[(S) + 33u + lane]; \
             }                                                                                     \
         }                                                                                         \
         if (lane0) {                                                                              \
@@ -534,11 +580,24 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     }
 
     for (uint32_t s = 0; s < nsteps; s += U) {
-        if (WAVE && !first) {
+        if (WRING && !first) {
+            if ((s & 31u) == kWavePf) {
+                const uint32_t base = (s & ~31u) + 32u;       // first entry of the next batch
+                if (base < X) {
+                    const uint32_t need = base + 32u < X ? base + 32u : X;
+                    if (avail < need) {
+                        if (lane0) avail = wait_progress(prog_in, need);
+                        avail = __shfl_sync(0xffffffffu, avail, 0);
+                        __syncwarp();
+                    }
+                    if (base + (uint32_t)lane < X) ring_nxt = __ldcg(scratch + base + lane);
+                }
+            }
+        } else if (WAVE && !first) {
             // this group prefetches boundary entries up to index s + U
             const uint32_t need = s + U + 1u < X ? s + U + 1u : X;
             if (avail < need) {
-                if (lane0) while ((avail = ld_acquire_u32(prog_in)) < need) {}
+                if (lane0) avail = wait_progress(prog_in, need);
                 avail = __shfl_sync(0xffffffffu, avail, 0);
             }
         }
@@ -549,7 +608,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         uint32_t any = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            nb[u] = ld_code(p + U + u);   // prefetch the next group's residues
+            nb[PD - 1][u] = ld_code(p + PD * U + u);   // prefetch the residues of the group PD ahead
             any |= b[u];
         }
         p += U;
@@ -567,7 +626,12 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) b[u] = nb[u];
+        for (int u = 0; u < U; ++u) b[u] = nb[0][u];
+#pragma unroll
+        for (int g = 0; g + 1 < PD; ++g) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) nb[g][u] = nb[g + 1][u];
+        }
     }
 #undef BSA_STEP
 #undef BSA_STEP_FAST
@@ -1538,8 +1602,18 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
 // order from a global counter, so the block to the left of a claimed item is always already
 // running (or done) and the spin-wait on its progress counter cannot deadlock.  The column
 // blocks of one pair thus sweep the DP matrix as a staggered wavefront over many SMs.
-constexpr int kWaveK = 8;        // 256 columns per block
-constexpr int kWaveWarps = 8;
+#ifndef BSA_WAVE_K
+#define BSA_WAVE_K 8
+#endif
+#ifndef BSA_WAVE_WARPS
+#define BSA_WAVE_WARPS 8
+#endif
+#ifndef BSA_WAVE_CTAS_PER_SM
+#define BSA_WAVE_CTAS_PER_SM 1
+#endif
+constexpr int kWaveK = BSA_WAVE_K;        // 32 K columns per block (256)
+constexpr int kWaveWarps = BSA_WAVE_WARPS;
+constexpr int kWaveCtasPerSm = BSA_WAVE_CTAS_PER_SM;   // the wavefront is bound by its critical path: fewer warps per scheduler = faster rows
 
 __global__ void __launch_bounds__(kWaveWarps * 32) gotoh_wave_kernel(const KArgs a) {
     extern __shared__ uint4 smem[];

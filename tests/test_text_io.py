@@ -206,7 +206,7 @@ def test_cli_end_to_end_on_gpu(ctx, tmp_path, oracle_matrices):
     ident[ref["q"], ref["t"]] = ref["identity"]
     ident = np.maximum(ident, ident.T)
     dist = (f32(100.0) - ident).astype(f32)
-    root, _ = pyhclust.hierarchical_clustering(n, lambda i, j: dist[i, j], "average_link")
+    root, _ = pyhclust.hierarchical_clustering(n, lambda i, j: dist[i, j], "average")
     cls = pyhclust.retrieve_clusters(root, f32(60.0))
     cls.sort(key=lambda c: c.cluster_size)
     for i, c in enumerate(cls):
