@@ -303,11 +303,13 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         std::vector<uint2> wave_items;      // (rec index, column block) in dependency order
         uint64_t dir_words = 0, scr_entries = 0, path_bytes = 0, n_prog = 0;
         // K3: templates this long run their column blocks as a wavefront over many warps
-        const int wave_warps = (int)std::min<size_t>(kWaveWarps, kSmemBudget / ((size_t)(C + 2) * KTraits<kWaveK>::ROW * sizeof(uint4)));
+        const int wave_warps = (int)std::min<size_t>(kWaveWarps, kSmemBudget / (wave_smem_u4(kWaveK, C) * sizeof(uint4)));
         while (pos < order.size()) {
             const PairReq& r = reqs[order[pos]];
             const uint64_t n = Q.len(r.q), m = T.len(r.t);
-            const bool wave = !local && m >= 4096 && wave_warps >= 1;   // >= 16 column blocks of 256 (kWaveK = 8)
+            const bool wave = !local && m >= 4096 && wave_warps >= 1 &&
+                              (!BSA_WAVE_P16 || (ctx->max_m <= 8000 && ctx->min_m >= -8000));   // 16-bit profile entries hold score * 4 + 3
+              // >= 16 column blocks of 256 (kWaveK = 8)
             const int K = wave ? kWaveK : choose_dirs_k(m, C);
             if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
             const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
@@ -426,7 +428,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             a.dirs = ctx->dirs.as<uint32_t>();
             a.progress = ctx->progress.as<uint32_t>();
             a.wave_items = ctx->wave_items.as<uint2>();
-            const size_t smem = (size_t)wave_warps * (C + 2) * KTraits<kWaveK>::ROW * sizeof(uint4);
+            const size_t smem = (size_t)wave_warps * wave_smem_u4(kWaveK, C) * sizeof(uint4);
             CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, smem));

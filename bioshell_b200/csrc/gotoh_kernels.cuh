@@ -52,6 +52,9 @@
 #ifndef BSA_WAVE_RING
 #define BSA_WAVE_RING 1     // K3: warp-wide batches of 32 boundary entries instead of lane 0's per-step load (one L2 round trip per row); 0: A/B only
 #endif
+#ifndef BSA_WAVE_P16
+#define BSA_WAVE_P16 0      // K3: 16-bit profile entries (half the shared memory per warp -> twice the warps per SM); NOT yet measured
+#endif
 #ifndef BSA_WAVE_POLL
 #define BSA_WAVE_POLL 0     // K3: poll the hand-off counter with relaxed loads (+ nanosleep) and acquire once, instead of an acquire (= L1 invalidate) per poll
 #endif
@@ -328,6 +331,23 @@ __device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict_
     }
 }
 
+// Same row from a 16-bit profile: 8 entries per uint4, [code][v16][lane]; entry c of a lane sits in
+// half (c & 1) of word (c >> 1) & 3 of vector c >> 3.
+template <int K>
+__device__ __forceinline__ void load_vec16(int (&dst)[K], const uint4* __restrict__ src) {
+    constexpr int V16 = (K + 7) / 8;
+#pragma unroll
+    for (int v = 0; v < V16; ++v) {
+        const uint4 x = src[v * 32];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (8 * v + 2 * e + 0 < K) dst[8 * v + 2 * e + 0] = (int)(short)(w[e] & 0xffffu);
+            if (8 * v + 2 * e + 1 < K) dst[8 * v + 2 * e + 1] = (int)w[e] >> 16;
+        }
+    }
+}
+
 // One systolic step of one lane: a row of K cells.  Hold = H of the previous row in this
 // lane's columns, Hnew = H of this row (the caller ping-pongs the two arrays so no register
 // copies are needed).  `one` is the runtime constant 1: `x * one + y` keeps the two plain
@@ -426,7 +446,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // HALF: two templates share the warp (lanes 0-15 / 16-31, see gotoh_pair_kernel); lane_last,
 // slot_last and out_idx0 are then per-lane values and positions count from the half's first lane.
 template <int K, bool DIRS, bool MULTI, bool WAVE = false, bool LOCAL = false, bool HALF = false,
-          bool TAG = false>
+          bool TAG = false, bool P16 = false>
 __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, uint64_t g0,
                                              uint64_t g1, const uint4* prof, const uint4* rsH,
                                              const uint4* rsF, const int lane, const bool first,
@@ -442,7 +462,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                                              const uint32_t colbase = 0, const int one2 = 1) {
     static_assert(!TAG || (!DIRS && !LOCAL && !WAVE), "the TAG cell carries no direction bits");
     constexpr int W = KTraits<K>::W;
-    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int ROWB = (P16 ? ((K + 7) / 8) * 32 : KTraits<K>::ROW) * (int)sizeof(uint4);
     if (!WAVE) scratch_out = scratch;
     uint32_t avail = 0;   // WAVE: boundary entries known to be published by the left block
     constexpr int U = (DIRS || MULTI) ? 2 : (K <= 10 ? 4 : 2);
@@ -505,7 +525,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 
     // one step; HO = previous row, HN = this row
 #define BSA_STEP_CORE(HO, HN, B, S)                                                               \
-        load_vec<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB));       \
+        if (P16) load_vec16<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB)); \
+        else load_vec<K>(T, reinterpret_cast<const uint4*>(prof_lane + ((B)&kCodeMask) * ROWB));  \
         int hin = __shfl_up_sync(0xffffffffu, oh, 1);                                             \
         int er = __shfl_up_sync(0xffffffffu, oe, 1);                                              \
         if (RING && !first) {                                                                     \
@@ -1611,6 +1632,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
 #ifndef BSA_WAVE_CTAS_PER_SM
 #define BSA_WAVE_CTAS_PER_SM 1
 #endif
+// shared memory of one wavefront worker (uint4 units): C profile rows + the two border rows
+__host__ __device__ constexpr int wave_prof_row(int K) { return BSA_WAVE_P16 ? ((K + 7) / 8) * 32 : ((K + 3) / 4) * 32; }
+__host__ __device__ constexpr size_t wave_smem_u4(int K, int C) {
+    return BSA_WAVE_P16 ? (size_t)C * wave_prof_row(K) + 2u * (size_t)(((K + 3) / 4) * 32)
+                        : (size_t)(C + 2) * (((K + 3) / 4) * 32);
+}
 constexpr int kWaveK = BSA_WAVE_K;        // 32 K columns per block (256)
 constexpr int kWaveWarps = BSA_WAVE_WARPS;
 constexpr int kWaveCtasPerSm = BSA_WAVE_CTAS_PER_SM;   // the wavefront is bound by its critical path: fewer warps per scheduler = faster rows
@@ -1620,11 +1647,13 @@ __global__ void __launch_bounds__(kWaveWarps * 32) gotoh_wave_kernel(const KArgs
     constexpr int K = kWaveK;
     constexpr int ROW = KTraits<K>::ROW;
     constexpr int W = KTraits<K>::W;
+    constexpr bool P16 = BSA_WAVE_P16 != 0;
+    constexpr int PROW = wave_prof_row(K);      // uint4 per profile row (16-bit entries: 8 per uint4)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int C = a.C;
-    uint4* prof = smem + (size_t)warp * (C + 2) * ROW;
-    uint4* rsH = prof + (size_t)C * ROW;
+    uint4* prof = P16 ? smem + (size_t)warp * wave_smem_u4(K, C) : smem + (size_t)warp * (C + 2) * ROW;
+    uint4* rsH = P16 ? prof + (size_t)C * PROW : prof + (size_t)C * ROW;
     uint4* rsF = rsH + ROW;
     const Consts cs = make_consts<K>(a.go, a.ge, 0);
     const int S = 4, P3 = 3;
@@ -1647,6 +1676,25 @@ __global__ void __launch_bounds__(kWaveWarps * 32) gotoh_wave_kernel(const KArgs
 
         // warp-private profile of this column block (same layout as build_profile)
         __syncwarp();
+        if (P16) {
+            for (int idx = lane; idx < C * PROW; idx += 32) {
+                const int code = idx / PROW, r = idx - code * PROW, v = r >> 5, ln = r & 31;
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint32_t h2[2];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int c = 8 * v + 2 * e + hh;
+                        const uint32_t col = colbase + ln * K + c;
+                        const int val = (c < K && col < m) ? (int)a.subst[code * C + (tc[col] & kCodeMask)] * S + P3 : cs.T_PAD;
+                        h2[hh] = (uint32_t)val & 0xffffu;      // |score * 4 + 3| < 2^15 (host range check on the matrix)
+                    }
+                    o[e] = h2[0] | (h2[1] << 16);
+                }
+                prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        } else
         for (int idx = lane; idx < C * ROW; idx += 32) {
             const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
             int o[4];
@@ -1680,7 +1728,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) gotoh_wave_kernel(const KArgs
         uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 32) * 32 * W;
         uint2* bnd = a.scratch + pr.scr_off;          // (npass - 1) boundary columns of n entries
         uint32_t* prog = a.progress + pr.prog_off;
-        stream_block<K, true, true, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
+        stream_block<K, true, true, true, false, false, false, P16>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
                                           lastp ? lane_last : 31, slot_last, hdiag0, cs, a.one,
                                           pass ? bnd + (size_t)(pass - 1) * n : nullptr, a.scores, nullptr,
                                           pr.out, dirs, lastp ? nullptr : bnd + (size_t)pass * n,
