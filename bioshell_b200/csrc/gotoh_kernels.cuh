@@ -53,7 +53,7 @@
 #define BSA_WAVE_RING 1     // K3: warp-wide batches of 32 boundary entries instead of lane 0's per-step load (one L2 round trip per row); 0: A/B only
 #endif
 #ifndef BSA_WAVE_P16
-#define BSA_WAVE_P16 0      // K3: 16-bit profile entries (half the shared memory per warp -> twice the warps per SM); NOT yet measured
+#define BSA_WAVE_P16 0      // K3: 16-bit profile entries (half the shared memory per warp -> 16 warps per SM): bit-exact, measured slower (28.0 vs 24.9 ms on cfg5), off
 #endif
 #ifndef BSA_WAVE_POLL
 #define BSA_WAVE_POLL 0     // K3: poll the hand-off counter with relaxed loads (+ nanosleep) and acquire once, instead of an acquire (= L1 invalidate) per poll
