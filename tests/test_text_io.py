@@ -180,6 +180,18 @@ def test_cli_arguments_match_the_reference_binary():
     assert (a.bucket_clustering, a.n_threads, a.detect_outliers) == (0.8, 4, 30.0)
 
 
+def test_cli_fails_loudly_without_a_device(tmp_path):
+    from bioshell_b200 import _lib
+    if _lib.lib().bsa_device_count() > 0:
+        pytest.skip("a GPU is present")
+    p = tmp_path / "in.fasta"
+    p.write_text(">a\nMKVLA\n>b\nMKVLG\n")
+    with pytest.raises(bs.BsaError) as e:
+        cli.main([str(p), "--single-link", "-c", "40", "--prefix", str(tmp_path) + "/"])
+    assert "no CPU fallback" in str(e.value)
+    assert not list(tmp_path.glob("cluster_*"))
+
+
 @pytest.mark.gpu
 def test_cli_end_to_end_on_gpu(ctx, tmp_path, oracle_matrices):
     """FASTA file in, cluster / medoid / ordered FASTA and the labelled distance matrix out, against
