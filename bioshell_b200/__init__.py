@@ -11,3 +11,5 @@ from . import clustering  # noqa: F401,E402
 from . import bucket_clustering  # noqa: F401,E402
 from .fasta import FastaIterator, load_sequences  # noqa: F401,E402
 from .sequence_id import LabelStyle, SeqId, SeqIdList, parse_sequence_id, sequence_label  # noqa: F401,E402
+from .reporters import (IdentityMatrixReporter, PrintAsFasta, PrintAsPairwise,  # noqa: F401,E402
+                        ReportWithSequenceIdentity, SimilarityReport)
