@@ -1,7 +1,7 @@
 """bioshell_b200 -- B200-native (sm_100a) all-vs-all global alignment behind
 BioShell's aligner API.  See DESIGN.md; the C ABI is include/bioshell_align.h."""
 from ._lib import BsaError, LIB_PATH  # noqa: F401
-from .alignment import (AlignmentReporter, AlignmentStatistics, CollectReporter, Context,  # noqa: F401
+from .alignment import (AlignmentPath, AlignmentReporter, AlignmentStatistics, AlignmentStep, CollectReporter, Context,  # noqa: F401
                         GlobalAligner, LocalAlignment, MultiReporter, PairResults, SequenceIdentityMatrix,
                         align_all_pairs, align_all_vs_all, align_one_vs_many, align_pairs_batched,
                         aligned_sequences, aligned_strings, aligned_symbols, triangle_counts)

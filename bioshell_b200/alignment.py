@@ -5,6 +5,7 @@ alike:
   align_all_pairs          bioshell-seq/src/alignment/alignment_protocols.rs:83-115
   AlignmentReporter        bioshell-seq/src/alignment/alignment_reporter.rs:7-9
   AlignmentStatistics      bioshell-seq/src/alignment/alignment_statistics.rs:28-81
+  AlignmentStep / AlignmentPath  bioshell-seq/src/alignment/alignment_path.rs:7-115
   aligned_strings/_sequences  bioshell-seq/src/alignment/alignment_path.rs:161-204
   SequenceIdentityMatrix   bin/cluster_sequences.rs:77-130
 plus the new batched entry points the north star asks for (`align_all_vs_all`,
@@ -14,6 +15,7 @@ All alignment arithmetic happens in libbioshell_align.so on the GPU.  Nothing he
 falls back to a CPU aligner.
 """
 import ctypes as C
+import enum
 
 import numpy as np
 
@@ -185,6 +187,47 @@ def default_context():
 # ---------------------------------------------------------------------------
 # alignment_path.rs
 # ---------------------------------------------------------------------------
+class AlignmentStep(enum.Enum):
+    """alignment_path.rs:7-32: `Horizontal` consumes a template residue (gap in the query, printed
+    '-'), `Vertical` a query residue (gap in the template, '|'), `Match` both ('*')."""
+    Horizontal = "-"
+    Vertical = "|"
+    Match = "*"
+
+    def __str__(self):                                    # alignment_path.rs:34-47
+        return self.value
+
+    @classmethod
+    def try_from(cls, value):                             # alignment_path.rs:50-62
+        c = chr(value) if isinstance(value, int) else value
+        try:
+            return cls(c)
+        except ValueError:
+            raise ValueError("Invalid value for AlignmentStep")
+
+
+class AlignmentPath(str):
+    """alignment_path.rs:75-115.  A `str` of step glyphs -- what the GPU traceback writes and what
+    `AlignmentPath::to_string()` prints -- with the reference's constructors and iterator."""
+
+    @classmethod
+    def try_from(cls, s):                                 # alignment_path.rs:88-104
+        s = s.decode("latin-1") if isinstance(s, (bytes, bytearray)) else s
+        for c in s:
+            AlignmentStep.try_from(c)
+        return cls(s)
+
+    @classmethod
+    def from_attrs(cls, path):                            # alignment_path.rs:81
+        return cls("".join(str(AlignmentStep(st) if not isinstance(st, AlignmentStep) else st) for st in path))
+
+    def iter(self):                                       # alignment_path.rs:84
+        return (AlignmentStep(c) for c in self)
+
+    def to_string(self):
+        return str(self)
+
+
 def aligned_symbols(path, query, template, gap_symbol=ord("-")):
     """alignment_path.rs:117-139: '-' takes a template symbol, '|' a query symbol, '*' both."""
     p = np.frombuffer(path.encode() if isinstance(path, str) else bytes(path), np.uint8)
@@ -439,7 +482,7 @@ class LocalAlignment:
 
     def backtrace(self):
         """-> (path, query_start, template_start)  (local.rs:213-273)"""
-        return self._r["paths"][0].decode(), int(self._r["start_q"][0]), int(self._r["start_t"][0])
+        return AlignmentPath(self._r["paths"][0].decode()), int(self._r["start_q"][0]), int(self._r["start_t"][0])
 
     def recent_score(self):
         return int(self._r["score"][0])
@@ -471,7 +514,7 @@ class GlobalAligner:
         return self._score
 
     def backtrace(self):
-        return self._path.decode()
+        return AlignmentPath(self._path.decode())
 
     def recent_score(self):
         return self._score

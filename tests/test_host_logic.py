@@ -147,3 +147,17 @@ def test_synth_is_deterministic_and_shaped():
     assert len(lens) == 1000 and lens.min() >= 50 and lens.max() <= 500
     # golden checksum so the C generator cannot drift silently
     assert int(o[-1]) == 281827 and int(r.astype(np.uint64).sum()) == int(np.frombuffer(r.tobytes(), np.uint8).astype(np.uint64).sum())
+
+
+def test_alignment_path_and_step_types():
+    # alignment_path.rs:96-100 (doc-test), :50-62, :81-84
+    path = bs.AlignmentPath.try_from("**-**")
+    assert path.to_string() == "**-**" and path == "**-**"
+    assert list(path.iter()) == [bs.AlignmentStep.Match, bs.AlignmentStep.Match, bs.AlignmentStep.Horizontal,
+                                 bs.AlignmentStep.Match, bs.AlignmentStep.Match]
+    assert bs.aligned_strings(path, "ALIV", "ALRIV", "-") == ("AL-IV", "ALRIV")     # alignment_path.rs:153-159
+    assert [str(s) for s in (bs.AlignmentStep.Horizontal, bs.AlignmentStep.Vertical, bs.AlignmentStep.Match)] == ["-", "|", "*"]
+    assert bs.AlignmentStep.try_from(ord("|")) is bs.AlignmentStep.Vertical
+    with pytest.raises(ValueError, match="Invalid value for AlignmentStep"):
+        bs.AlignmentPath.try_from("**x*")
+    assert bs.AlignmentPath.from_attrs([bs.AlignmentStep.Match, bs.AlignmentStep.Vertical]) == "*|"
