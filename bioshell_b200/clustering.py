@@ -187,44 +187,50 @@ def retrieve_clusters(clustering_root, max_distance):
     return clusters
 
 
-def _leftmost(c):
-    while c._left is not None:
-        c = c._left
-    return c.id
-
-
-def _rightmost(c):
-    while c._right is not None:
-        c = c._right
-    return c.id
-
-
-def _if_rotate(c, distance):
-    """hierarchical.rs:242-287"""
-    if c.is_leaf():
-        return False, False
-    left, right = c._left, c._right
+def _if_rotate(left, right, lm, rm, distance):
+    """hierarchical.rs:242-287 on cached leftmost / rightmost leaf ids (lm / rm, by node)."""
     if right.is_leaf() and left.is_leaf():
         return False, False
     if right.is_leaf():
-        return bool(distance(right.id, _leftmost(left)) < distance(right.id, _rightmost(left))), False
+        return bool(distance(right.id, lm[left]) < distance(right.id, rm[left])), False
     if left.is_leaf():
-        return False, bool(distance(left.id, _leftmost(right)) > distance(left.id, _rightmost(right)))
-    rr, rl, lr, ll = _rightmost(right), _leftmost(right), _rightmost(left), _leftmost(left)
+        return False, bool(distance(left.id, lm[right]) > distance(left.id, rm[right]))
+    rr, rl, lr, ll = rm[right], lm[right], rm[left], lm[left]
     d = [distance(lr, rl), distance(ll, rl), distance(lr, rr), distance(ll, rr)]
     k = min(range(4), key=lambda t: (d[t], t))    # Iterator::min_by returns the first minimum
     return ((False, False), (True, False), (False, True), (True, True))[k]
 
 
 def balance_clustering_tree(root, distance):
-    """hierarchical.rs:86-100: post-order, rotate children to bring similar leaves together."""
-    # children before parents, left subtree before right subtree (rotate_rec order)
-    for nd in _postorder(root):
-        a, b = _if_rotate(nd, distance)
+    """hierarchical.rs:86-100: post-order, mirror a child's subtree (`rotate`, tree.rs:106-118) to
+    bring similar leaves together.  Same decisions and same final tree as the reference, in O(n):
+    the reference walks to the outermost leaves at every node and mirrors subtrees eagerly (both
+    O(subtree), quadratic on the chain-like trees single linkage produces); here the outermost
+    leaf ids are cached per node and a mirror is a pending flag pushed down once at the end."""
+    lm, rm, flip = {}, {}, {}
+    for nd in _postorder(root):                  # children before parents, left subtree first
+        if nd.is_leaf():
+            lm[nd] = rm[nd] = nd.id
+            continue
+        left, right = nd._left, nd._right        # nobody above has mirrored nd yet (post-order)
+        a, b = _if_rotate(left, right, lm, rm, distance)
         if a:
-            nd._left.rotate()
+            flip[left] = not flip.get(left, False)
+            lm[left], rm[left] = rm[left], lm[left]
         if b:
-            nd._right.rotate()
+            flip[right] = not flip.get(right, False)
+            lm[right], rm[right] = rm[right], lm[right]
+        lm[nd], rm[nd] = lm[left], rm[right]
+    stack = [(root, False)]                      # push the pending mirrors down
+    while stack:
+        nd, mirrored = stack.pop()
+        mirrored ^= flip.get(nd, False)
+        if mirrored:
+            nd._left, nd._right = nd._right, nd._left
+        if nd._left is not None:
+            stack.append((nd._left, mirrored))
+        if nd._right is not None:
+            stack.append((nd._right, mirrored))
 
 
 def _postorder(root):

@@ -106,3 +106,52 @@ def test_fasta_display_format():
     s = Sequence("2gb1", "MTYKLILNGKTLKGETTTEAVDAATAEKVFKQYANDNGVDGEWTYDDATKTFTVTE")
     # bioshell-seq/src/sequence/display_sequence.rs:22
     assert cl.format_fasta(s) == "> 2gb1\nMTYKLILNGKTLKGETTTEAVDAATAEKVFKQYANDNGVDGEWTYDDATKTFTVTE\n"
+
+
+def _product_tree_from_oracle(n, dist, rule):
+    """The product's tree classes built from the oracle's merge log (no GPU involved)."""
+    from bioshell_b200 import clustering as cl
+    root, log = pyhclust.hierarchical_clustering(n, lambda i, j: dist[i, j], rule)
+    mi = np.array([e[0] for e in log], np.uint32)
+    mj = np.array([e[1] for e in log], np.uint32)
+    md = np.array([e[4] for e in log], np.float32)
+    return cl.tree_from_merge_log(n, mi, mj, md), root
+
+
+def _shape(nd, left, right):
+    """nested tuple of leaf ids / children, iterative-safe for the small trees used here"""
+    if left(nd) is None and right(nd) is None:
+        return nd.id
+    return (_shape(left(nd), left, right), _shape(right(nd), left, right))
+
+
+@pytest.mark.parametrize("rule", ["single", "complete", "average"])
+def test_linear_time_balance_equals_the_literal_one(rule):
+    """balance_clustering_tree with cached outermost leaves and deferred mirrors (product) against
+    the literal recursive restatement of hierarchical.rs:86-100,242-287 (oracle), tie-rich input."""
+    from bioshell_b200 import clustering as cl
+    rng = np.random.default_rng(5)
+    for n, levels in ((2, 3), (3, 2), (17, 4), (64, 6), (150, 1000)):
+        d = rng.integers(0, levels, (n, n)).astype(np.float32)
+        d = np.maximum(d, d.T)
+        tree, oroot = _product_tree_from_oracle(n, d, rule)
+        assert _shape(tree, lambda x: x._left, lambda x: x._right) == _shape(oroot, lambda x: x.left, lambda x: x.right)
+        cl.balance_clustering_tree(tree, lambda i, j: d[i, j])
+        pyhclust.balance_clustering_tree(oroot, lambda i, j: d[i, j])
+        assert _shape(tree, lambda x: x._left, lambda x: x._right) == _shape(oroot, lambda x: x.left, lambda x: x.right)
+        assert cl.retrieve_data_id(tree) == pyhclust.retrieve_data_id(oroot)
+
+
+def test_tree_functions_survive_a_deep_chain():
+    """Single linkage produces chain-like trees; 30,000 levels must neither recurse nor go quadratic."""
+    import time
+    from bioshell_b200 import clustering as cl
+    n = 30000
+    mi, mj = np.zeros(n - 1, np.uint32), np.ones(n - 1, np.uint32)
+    md = np.arange(n - 1, dtype=np.float32)
+    root = cl.tree_from_merge_log(n, mi, mj, md)
+    t0 = time.perf_counter()
+    cl.balance_clustering_tree(root, lambda i, j: float(abs(i - j)))
+    assert time.perf_counter() - t0 < 5.0
+    assert sorted(cl.retrieve_data_id(root)) == list(range(n))
+    assert len(cl.retrieve_clusters(root, np.float32(n / 2))) > 1
