@@ -267,6 +267,22 @@ def medoid_by_min_max(cluster, distance_fn):
     return members[best_index]
 
 
+def medoid_by_min_max_matrix(cluster, dist):
+    """`medoid_by_min_max` when the distances are an n x n array (`distance_fn(i, j) = dist[i, j]`):
+    the same first-minimum of the row maxima, as array operations instead of m^2 closure calls."""
+    members = retrieve_data_id(cluster)
+    if len(members) == 1:
+        return members[0]
+    fmax = np.finfo(np.float32).max
+    idx = np.asarray(members)
+    sub = np.array(dist[np.ix_(idx, idx)], np.float32)
+    sub[np.isnan(sub)] = -fmax                   # `d > mx` is false for a NaN: it never raises the maximum
+    np.fill_diagonal(sub, -fmax)                 # i != j
+    mx = sub.max(axis=1)
+    best = int(np.argmin(mx))                    # first minimum, like the strict `mx < best`
+    return members[best] if mx[best] < fmax else members[0]
+
+
 def retrieve_outliers(n_data, distance_fn, cutoff):
     """hierarchical.rs:198-217"""
     out = []
@@ -338,7 +354,7 @@ def cluster_sequences(sequences, linkage, gap_open=-10, gap_extend=-2, identity_
                     for sid in retrieve_data_id(c):
                         fh.write(format_fasta(sequences[sid], sequence_width) + "\n")
         if medoids:
-            out["medoids"] = [medoid_by_min_max(c, distance_fn) for c in clusters]
+            out["medoids"] = [medoid_by_min_max_matrix(c, dist) for c in clusters]
             if write_files:
                 for i, c in enumerate(clusters):
                     with open("%scenter_%d-%d.fasta" % (prefix, i, c.value.cluster_size), "w") as fh:

@@ -155,3 +155,18 @@ def test_tree_functions_survive_a_deep_chain():
     assert time.perf_counter() - t0 < 5.0
     assert sorted(cl.retrieve_data_id(root)) == list(range(n))
     assert len(cl.retrieve_clusters(root, np.float32(n / 2))) > 1
+
+
+def test_matrix_medoid_equals_the_closure_one():
+    from bioshell_b200 import clustering as cl
+    rng = np.random.default_rng(11)
+    for n, levels in ((1, 2), (2, 2), (9, 3), (40, 4), (80, 1000)):
+        d = rng.integers(0, levels, (n, n)).astype(np.float32)          # asymmetric on purpose, many ties
+        if n > 5:
+            d[3, 4] = np.nan
+        sym = np.maximum(d, d.T) if n > 1 else d
+        sym = np.nan_to_num(sym, nan=1.0)
+        tree, _ = (_product_tree_from_oracle(n, sym, "average") if n > 1 else
+                   (cl.tree_from_merge_log(1, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32)), None))
+        for c in [tree] + cl.retrieve_clusters(tree, np.float32(levels / 2)):
+            assert cl.medoid_by_min_max_matrix(c, d) == cl.medoid_by_min_max(c, lambda i, j: d[i, j])
