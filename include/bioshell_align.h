@@ -196,8 +196,9 @@ int bsa_get_stats(const bsa_ctx *ctx, bsa_stats *out);
  * kernel's own instruction mix (VIADDMNMX / VIMNMX3 / LOP3 / IADD3) on every SM.
  * Returns lane-operations per second (32 x warp instructions); this is the
  * measured denominator of the integer/DPX roofline.
- * which: 0 = the 8-op cell mix, 1 = VIADDMNMX only, 2 = VIMNMX3 only, 3 = LOP3 only,
- *        4 = IADD3 only, 5 = IMAD only, 6 = VIADDMNMX.S16x2 only
+ * which: 0 = the 8-op classic cell mix, 1 = VIADDMNMX only, 2 = VIMNMX3 only, 3 = LOP3 only,
+ *        4 = IADD3 only, 5 = IMAD only, 6 = VIADDMNMX.S16x2 only,
+ *        7 = the 7-op TAG cell mix (VIMNMX3 + LOP3 + 2 VIADDMNMX + 3 IMAD; what bench.py uses)
  */
 int bsa_measure_int_peak(bsa_ctx *ctx, int which, double *lane_ops_per_s, double *sm_clock_mhz);
 

@@ -24,6 +24,16 @@ extern "C" {
     fn bsa_align_pairs_paths(ctx: *mut BsaCtx, q_set: c_int, t_set: c_int, q_idx: *const u32, t_idx: *const u32,
                              n_pairs: u64, scores: *mut i32, n_identical: *mut u32, path_buf: *mut u8,
                              path_off: *mut u64) -> c_int;
+    fn bsa_all_vs_all(ctx: *mut BsaCtx, set_id: c_int, flags: u32, scores: *mut i32, n_identical: *mut u32) -> c_int;
+    fn bsa_one_vs_many(ctx: *mut BsaCtx, q_set: c_int, db_set: c_int, flags: u32, scores: *mut i32,
+                       n_identical: *mut u32) -> c_int;
+    fn bsa_plan_shards(ctx: *mut BsaCtx, q_set: c_int, t_set: c_int, q_counts: *const u32, n_shards: u32,
+                       bounds: *mut u32) -> c_int;
+    fn bsa_local_align_pairs(ctx: *mut BsaCtx, q_set: c_int, t_set: c_int, q_idx: *const u32, t_idx: *const u32,
+                             n_pairs: u64, scores: *mut i32, end_q: *mut u32, end_t: *mut u32, start_q: *mut u32,
+                             start_t: *mut u32, path_buf: *mut u8, path_off: *mut u64) -> c_int;
+    fn bsa_hclust(ctx: *mut BsaCtx, n: u32, dist: *const f32, linkage: c_int, flags: u32, mat_i: *mut u32,
+                  mat_j: *mut u32, merge_dist: *mut f32) -> c_int;
 }
 
 const BSA_WANT_SCORE: u32 = 1;
@@ -125,6 +135,94 @@ impl GpuAligner {
             }
         }
         Ok(())
+    }
+}
+
+/// One local alignment as `LocalAlignment::{recent_score, recent_end_point, backtrace}` report it
+/// (bioshell-seq/src/alignment/local.rs:205-284).
+pub struct LocalHit {
+    pub score: i32,
+    pub end: (u32, u32),
+    pub start: (u32, u32),
+    pub path: AlignmentPath,
+}
+
+/// Linkage codes of `bsa_hclust`, in the order of bioshell-clustering/src/hierarchical/strategies/mod.rs:25-92.
+#[derive(Clone, Copy)]
+pub enum Linkage { Single = 0, Complete = 1, Average = 2, Median = 3, Centroid = 4, Ward = 5 }
+
+impl GpuAligner {
+    /// Score-only search of every query against every database sequence (needleman_wunsh.rs:108-109
+    /// without the strings): result k = t * |queries| + q.
+    pub fn align_one_vs_many(&self, queries: &[Sequence], database: &[Sequence], matrix: SubstitutionMatrixList,
+                             gap_open: i32, gap_extend: i32) -> Result<Vec<i32>, String> {
+        let m = SubstitutionMatrix::load(matrix);
+        let mut aa = [0u8; 256];
+        aa[..255].copy_from_slice(&m.aa_indexes);
+        self.check(unsafe { bsa_set_scoring(self.ctx, m.score.as_ptr(), aa.as_ptr(), gap_open, gap_extend) })?;
+        self.load(0, queries)?;
+        self.load(1, database)?;
+        let mut scores = vec![0i32; queries.len() * database.len()];
+        self.check(unsafe { bsa_one_vs_many(self.ctx, 0, 1, BSA_WANT_SCORE, scores.as_mut_ptr(), std::ptr::null_mut()) })?;
+        Ok(scores)
+    }
+
+    /// Strict upper triangle of one loaded set (the `cluster_sequences` call): k = t (t - 1) / 2 + q.
+    pub fn all_vs_all_loaded(&self, n: usize) -> Result<(Vec<i32>, Vec<u32>), String> {
+        let pairs = n * (n - 1) / 2;
+        let (mut scores, mut nid) = (vec![0i32; pairs], vec![0u32; pairs]);
+        self.check(unsafe {
+            bsa_all_vs_all(self.ctx, 0, BSA_WANT_SCORE | BSA_WANT_IDENTICAL, scores.as_mut_ptr(), nid.as_mut_ptr())
+        })?;
+        Ok((scores, nid))
+    }
+
+    /// Cell-balanced template ranges for `n_shards` processes, one GPU each; shard r then calls
+    /// `bsa_align_all_pairs(.., bounds[r], bounds[r + 1], ..)`.  No collective is involved.
+    pub fn plan_shards(&self, q_counts: &[u32], n_shards: u32) -> Result<Vec<u32>, String> {
+        let mut bounds = vec![0u32; n_shards as usize + 1];
+        self.check(unsafe { bsa_plan_shards(self.ctx, 0, 1, q_counts.as_ptr(), n_shards, bounds.as_mut_ptr()) })?;
+        Ok(bounds)
+    }
+
+    /// `LocalAlignment::align` + `backtrace` + `recent_end_point` for a list of (query, template) index pairs
+    /// of the loaded sets 0 and 1.
+    pub fn local_align_pairs(&self, queries: &[Sequence], templates: &[Sequence], pairs: &[(u32, u32)])
+            -> Result<Vec<LocalHit>, String> {
+        let n = pairs.len();
+        let q_idx: Vec<u32> = pairs.iter().map(|p| p.0).collect();
+        let t_idx: Vec<u32> = pairs.iter().map(|p| p.1).collect();
+        let cap: usize = pairs.iter().map(|p| queries[p.0 as usize].len() + templates[p.1 as usize].len()).sum();
+        let (mut scores, mut path_buf, mut path_off) = (vec![0i32; n], vec![0u8; cap.max(1)], vec![0u64; n + 1]);
+        let (mut eq, mut et, mut sq, mut st) = (vec![0u32; n], vec![0u32; n], vec![0u32; n], vec![0u32; n]);
+        self.check(unsafe {
+            bsa_local_align_pairs(self.ctx, 0, 1, q_idx.as_ptr(), t_idx.as_ptr(), n as u64, scores.as_mut_ptr(),
+                                  eq.as_mut_ptr(), et.as_mut_ptr(), sq.as_mut_ptr(), st.as_mut_ptr(),
+                                  path_buf.as_mut_ptr(), path_off.as_mut_ptr())
+        })?;
+        Ok((0..n).map(|k| {
+            let glyphs = std::str::from_utf8(&path_buf[path_off[k] as usize..path_off[k + 1] as usize]).unwrap();
+            LocalHit { score: scores[k], end: (eq[k], et[k]), start: (sq[k], st[k]),
+                       path: AlignmentPath::try_from(glyphs).unwrap() }
+        }).collect())
+    }
+
+    /// The merge log of `hierarchical_clustering` (bioshell-clustering/src/hierarchical/hierarchical.rs:22-80):
+    /// per step the two matrix indices `closest_elements` returned and their distance; the caller replays
+    /// hierarchical.rs:44-75 on it to build the `BinaryTreeNode<HierarchicalCluster>` tree.
+    /// `dist` is n x n row-major, only dist[i * n + j] with i > j is read (clustering_matrix.rs:14-19).
+    pub fn hclust_merge_log(&self, n: usize, dist: &[f32], linkage: Linkage) -> Result<(Vec<u32>, Vec<u32>, Vec<f32>), String> {
+        assert_eq!(dist.len(), n * n);
+        let k = n.saturating_sub(1).max(1);
+        let (mut mi, mut mj, mut md) = (vec![0u32; k], vec![0u32; k], vec![0f32; k]);
+        self.check(unsafe {
+            bsa_hclust(self.ctx, n as u32, dist.as_ptr(), linkage as c_int, 0, mi.as_mut_ptr(), mj.as_mut_ptr(),
+                       md.as_mut_ptr())
+        })?;
+        mi.truncate(n.saturating_sub(1));
+        mj.truncate(n.saturating_sub(1));
+        md.truncate(n.saturating_sub(1));
+        Ok((mi, mj, md))
     }
 }
 
