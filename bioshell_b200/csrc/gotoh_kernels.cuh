@@ -55,6 +55,12 @@
 #ifndef BSA_WAVE_P16
 #define BSA_WAVE_P16 0      // K3: 16-bit profile entries (half the shared memory per warp -> 16 warps per SM): bit-exact, measured slower (28.0 vs 24.9 ms on cfg5), off
 #endif
+#ifndef BSA_WAVE_BATCH
+#define BSA_WAVE_BATCH 32   // K3: boundary entries per publication / per warp-wide fetch (32 or 16; 16 halves the hand-off lag, doubles the release fences): NOT yet measured
+#endif
+#ifndef BSA_WAVE_PF
+#define BSA_WAVE_PF 8       // K3: step inside a batch at which the next batch is fetched (even, < BSA_WAVE_BATCH); later = less lag: NOT yet measured
+#endif
 #ifndef BSA_WAVE_POLL
 #define BSA_WAVE_POLL 0     // K3: poll the hand-off counter with relaxed loads (+ nanosleep) and acquire once, instead of an acquire (= L1 invalidate) per poll
 #endif
@@ -439,6 +445,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+constexpr uint32_t kWavePub = (BSA_WAVE_RING && BSA_WAVE_BATCH == 16) ? 16u : 32u;   // rows per boundary publication
 // WAVE: the column blocks of one long pair run CONCURRENTLY in different warps (K3, the
 // intra-task wavefront).  The block to the left publishes how many boundary entries it has
 // written (`prog_out`, release store every 32 rows); this block waits on `prog_in` (acquire)
@@ -505,17 +512,20 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     // L2 round trip: ~830 cycles per row on B200.)
     constexpr bool WRING = MULTI && WAVE && BSA_WAVE_RING;
     constexpr bool RING = MULTI && ((!WAVE && BSA_RING) || WRING);
-    constexpr uint32_t kWavePf = 8;   // step inside a batch at which the next batch is fetched (even)
+    constexpr uint32_t kWavePf = BSA_WAVE_PF;   // step inside a batch at which the next batch is fetched (even)
+    constexpr uint32_t WB = WRING ? BSA_WAVE_BATCH : 32u;   // entries per batch (the non-WAVE ring always uses 32)
+    static_assert(BSA_WAVE_BATCH == 32 || BSA_WAVE_BATCH == 16, "batch of 32 or 16 boundary entries");
+    static_assert(BSA_WAVE_PF % 2 == 0 && BSA_WAVE_PF < BSA_WAVE_BATCH, "fetch step: even, inside the batch");
     uint2 ring_cur = make_uint2(0u, 0u), ring_nxt = make_uint2(0u, 0u);
     if (WAVE && !first && X > 0) {
-        const uint32_t need0 = WRING ? (X < 32u ? X : 32u) : 1u;
+        const uint32_t need0 = WRING ? (X < WB ? X : WB) : 1u;
         if (lane0) avail = wait_progress(prog_in, need0);
         avail = __shfl_sync(0xffffffffu, avail, 0);
         __syncwarp();
     }
     if (RING && !first) {
         if (WRING) {
-            if ((uint32_t)lane < X) ring_cur = __ldcg(scratch + lane);
+            if ((uint32_t)lane < X && (uint32_t)lane < WB) ring_cur = __ldcg(scratch + lane);
         } else {
             if ((uint32_t)lane < X) ring_cur = scratch[lane];
             if (32u + (uint32_t)lane < X) ring_nxt = scratch[32 + lane];
@@ -530,9 +540,9 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         int hin = __shfl_up_sync(0xffffffffu, oh, 1);                                             \
         int er = __shfl_up_sync(0xffffffffu, oe, 1);                                              \
         if (RING && !first) {                                                                     \
-            sc_next.x = __shfl_sync(0xffffffffu, ring_cur.x, (S)&31u);                            \
-            sc_next.y = __shfl_sync(0xffffffffu, ring_cur.y, (S)&31u);                            \
-            if (((S)&31u) == 31u) {                                                               \
+            sc_next.x = __shfl_sync(0xffffffffu, ring_cur.x, (S) & (WB - 1u));                    \
+            sc_next.y = __shfl_sync(0xffffffffu, ring_cur.y, (S) & (WB - 1u));                    \
+            if (((S) & (WB - 1u)) == WB - 1u) {                                                   \
                 ring_cur = ring_nxt;                                                              \
                 if (!WRING && (S) + 33u + (uint32_t)lane < X) ring_nxt = scratch[(S) + 33u + lane]; \
             }                                                                                     \
@@ -573,7 +583,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             const uint32_t pos = (S)-31u; /* wraps for S < 31 -> fails the bound test */          \
             if (pos < X) {                                                                        \
                 scratch_out[pos] = make_uint2((uint32_t)oh, (uint32_t)oe);                        \
-                if (WAVE && ((pos & 31u) == 31u || pos + 1u == X)) st_release_u32(prog_out, pos + 1u); \
+                if (WAVE && ((pos & (kWavePub - 1u)) == kWavePub - 1u || pos + 1u == X)) st_release_u32(prog_out, pos + 1u); \
             }                                                                                     \
         }
 #define BSA_STEP_FAST(HO, HN, B, S) { BSA_STEP_CORE(HO, HN, B, S) }
@@ -602,16 +612,16 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 
     for (uint32_t s = 0; s < nsteps; s += U) {
         if (WRING && !first) {
-            if ((s & 31u) == kWavePf) {
-                const uint32_t base = (s & ~31u) + 32u;       // first entry of the next batch
+            if ((s & (WB - 1u)) == kWavePf) {
+                const uint32_t base = (s & ~(WB - 1u)) + WB;       // first entry of the next batch
                 if (base < X) {
-                    const uint32_t need = base + 32u < X ? base + 32u : X;
+                    const uint32_t need = base + WB < X ? base + WB : X;
                     if (avail < need) {
                         if (lane0) avail = wait_progress(prog_in, need);
                         avail = __shfl_sync(0xffffffffu, avail, 0);
                         __syncwarp();
                     }
-                    if (base + (uint32_t)lane < X) ring_nxt = __ldcg(scratch + base + lane);
+                    if (base + (uint32_t)lane < X && (uint32_t)lane < WB) ring_nxt = __ldcg(scratch + base + lane);
                 }
             }
         } else if (WAVE && !first) {
