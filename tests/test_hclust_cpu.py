@@ -170,3 +170,22 @@ def test_matrix_medoid_equals_the_closure_one():
                    (cl.tree_from_merge_log(1, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32)), None))
         for c in [tree] + cl.retrieve_clusters(tree, np.float32(levels / 2)):
             assert cl.medoid_by_min_max_matrix(c, d) == cl.medoid_by_min_max(c, lambda i, j: d[i, j])
+
+
+def test_reference_balance_kats_through_the_product_tree_functions(kats):
+    """tests/test_hierarchical.rs:9-41 on the product's tree code (merge log from the oracle, no GPU)."""
+    from bioshell_b200 import clustering as cl
+    f32 = np.float32
+    k = kats["hierarchical_clustering"]
+    data = k["cluster_numbers"]["data"]
+    d = np.array([[abs(f32(a) - f32(b)) for b in data] for a in data], f32)
+    tree, _ = _product_tree_from_oracle(len(data), d, "single")
+    assert cl.retrieve_data(tree, data) == k["cluster_numbers"]["order"]
+    cl.balance_clustering_tree(tree, lambda i, j: d[i, j])
+    assert cl.retrieve_data(tree, data) == k["cluster_numbers"]["order_after_balance"]
+    letters = list(k["cluster_letters"]["data"])
+    d2 = np.array([[abs(ord(a) - ord(b)) for b in letters] for a in letters], f32)
+    tree, _ = _product_tree_from_oracle(len(letters), d2, "single")
+    assert "".join(cl.retrieve_data(tree, letters)) == k["cluster_letters"]["order"]
+    cl.balance_clustering_tree(tree, lambda i, j: d2[i, j])
+    assert "".join(cl.retrieve_data(tree, letters)) == k["cluster_letters"]["order_after_balance"]
