@@ -87,13 +87,3 @@ def test_cpp_clustering_mirror_tree_functions_match_oracle(tmp_path, rule):
         assert r.returncode == 0, r.stderr
         got = [ln.rstrip() for ln in r.stdout.strip().split("\n")]
         assert got == [w.rstrip() for w in want]
-
-
-@pytest.mark.gpu
-def test_cpp_clustering_mirror_on_gpu(tmp_path):
-    _build_if_missing()
-    for rule in ("single", "complete", "average"):
-        path, want = _clustering_case(tmp_path, 70, 5, rule, 7)
-        r = subprocess.run([CEXE, str(path), "--gpu"], capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stderr
-        assert [ln.rstrip() for ln in r.stdout.strip().split("\n")] == [w.rstrip() for w in want]

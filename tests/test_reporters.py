@@ -185,17 +185,3 @@ def _expected_text(oracle_matrices):
     _oracle_replay(oracle_matrices)(seqs, seqs, "BLOSUM62", -10, -2, True, m)
     im.finish()
     return want.getvalue()
-
-
-@pytest.mark.gpu
-def test_needleman_wunsh_cli_on_gpu(ctx, tmp_path, oracle_matrices):
-    got = io.StringIO()
-    _run_cli(tmp_path, NW_ARGS, got)
-    assert got.getvalue() == _expected_text(oracle_matrices)
-    # query set against a template set: every pair, self pairs included (if_triangle_only = false)
-    t = tmp_path / "t.fasta"
-    t.write_text(">t1\nMAVRLLKTHL\n>t2\nMKNITCYL\n")
-    got = io.StringIO()
-    _run_cli(tmp_path, ["-t", str(t), "--identity"], got)
-    assert len(got.getvalue().strip().split("\n")) == 8
-    assert np.all([ln.count("%") == 1 for ln in got.getvalue().strip().split("\n")])
