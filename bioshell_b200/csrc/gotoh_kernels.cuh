@@ -76,6 +76,16 @@
 #ifndef BSA_CHUNK_BIG
 #define BSA_CHUNK_BIG 4096  // stream residues per big chunk
 #endif
+#ifndef BSA_FLAG_LOOP
+#define BSA_FLAG_LOOP 0      // two-row blocks: the flagged branch as a rolled loop over its double steps (half the code of the slow path): NOT yet measured
+#endif
+#if BSA_FLAG_LOOP
+#define BSA_FLAG_UNROLL _Pragma("unroll 1")
+#define BSA_B(u, k) b[k]
+#else
+#define BSA_FLAG_UNROLL _Pragma("unroll")
+#define BSA_B(u, k) b[2 * (u) + (k)]
+#endif
 #ifndef BSA_FLAG_SPLIT
 #define BSA_FLAG_SPLIT 0     // two-row blocks: a flagged double step whose flags all sit on its second row keeps the interleaved form
 #endif
@@ -814,24 +824,28 @@ _Pragma("unroll")                                                               
                 BSA_PAIR2()
             }
         } else {
-#pragma unroll
+            BSA_FLAG_UNROLL
             for (int u = 0; u < U; ++u) {
                 const uint32_t pos0 = 2u * (S + u - (uint32_t)lrel);   // wraps below row 0: fails pos < X
-                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u] & kCodeMask) * ROWB));
-                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u + 1] & kCodeMask) * ROWB));
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (BSA_B(u, 0) & kCodeMask) * ROWB));
+                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (BSA_B(u, 1) & kCodeMask) * ROWB));
                 int hin0 = __shfl_up_sync(0xffffffffu, oh0, 1);
                 int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-                if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, b[2 * u] & kLastFlag)) {
+                if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, BSA_B(u, 0) & kLastFlag)) {
                     // flags only on the second row: the interleaved step stays valid, reset afterwards
                     BSA_PAIR2()
-                    BSA_FLAG1(b[2 * u + 1], pos0 + 1u)
+                    BSA_FLAG1(BSA_B(u, 1), pos0 + 1u)
                 } else {
                     BSA_ROW1(T0, hin0, er0, oh0, oe0)
-                    BSA_FLAG1(b[2 * u], pos0)
+                    BSA_FLAG1(BSA_B(u, 0), pos0)
                     BSA_ROW1(T1, hin1, er1, oh1, oe1)
-                    BSA_FLAG1(b[2 * u + 1], pos0 + 1u)
+                    BSA_FLAG1(BSA_B(u, 1), pos0 + 1u)
+                }
+                if (BSA_FLAG_LOOP) {   // rolled loop: the next double step's residues move to b[0], b[1]
+#pragma unroll
+                    for (int k = 0; k + 2 < 2 * U; ++k) b[k] = b[k + 2];
                 }
             }
         }
@@ -1344,23 +1358,27 @@ _Pragma("unroll")                                                               
                 BSA_PAIR16()
             }
         } else {
-#pragma unroll
+            BSA_FLAG_UNROLL
             for (int u = 0; u < U; ++u) {
                 const uint32_t pos0 = 2u * (S + u - (uint32_t)lane);
-                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u] & kCodeMask) * ROWB));
-                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b[2 * u + 1] & kCodeMask) * ROWB));
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + (BSA_B(u, 0) & kCodeMask) * ROWB));
+                load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (BSA_B(u, 1) & kCodeMask) * ROWB));
                 uint32_t hin0 = __shfl_up_sync(0xffffffffu, oh0, 1);
                 uint32_t e0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 uint32_t hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 uint32_t e1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-                if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, b[2 * u] & kLastFlag)) {
+                if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, BSA_B(u, 0) & kLastFlag)) {
                     BSA_PAIR16()
-                    BSA_FLAG16(b[2 * u + 1], pos0 + 1u)
+                    BSA_FLAG16(BSA_B(u, 1), pos0 + 1u)
                 } else {
                     BSA_ROW16(T0, hin0, e0, oh0, oe0)
-                    BSA_FLAG16(b[2 * u], pos0)
+                    BSA_FLAG16(BSA_B(u, 0), pos0)
                     BSA_ROW16(T1, hin1, e1, oh1, oe1)
-                    BSA_FLAG16(b[2 * u + 1], pos0 + 1u)
+                    BSA_FLAG16(BSA_B(u, 1), pos0 + 1u)
+                }
+                if (BSA_FLAG_LOOP) {
+#pragma unroll
+                    for (int k = 0; k + 2 < 2 * U; ++k) b[k] = b[k + 2];
                 }
             }
         }
