@@ -1,10 +1,9 @@
 """`cluster_sequences` -- the command line of the reference's bin/cluster_sequences.rs:18-74,133-261
 on the batched GPU path:  python -m bioshell_b200.cli <in.fasta> --single-link -c 40
 
-Same positional argument, options, defaults and output files as the reference binary.  Two
-options are additions: `--device` (which GPU) and `--symmetric` (mirror the identity matrix before
-clustering; without it the matrix stays exactly as the reference's reporter fills it, upper
-triangle only -- SURVEY.md 3.1 note).  There is no CPU fallback: without a B200 the alignment
+Same positional argument, options, defaults and output files as the reference binary.  Additions: `--device` (which GPU) and `--reference-compat` (the default) / `--symmetric` (mirror the
+identity matrix before clustering; without it the matrix stays exactly as the reference's reporter
+fills it, upper triangle only -- SURVEY.md 3.1 note).  There is no CPU fallback: without a B200 the alignment
 call fails.
 """
 import argparse
@@ -53,7 +52,11 @@ def build_parser():
                    help="length of a sequence itself to print; use 0 to print the whole sequence in a single line")
     p.add_argument("-v", "--verbose", action="store_true", help="be more verbose")
     p.add_argument("--device", type=int, default=0, help="(addition) CUDA device to run on")
-    p.add_argument("--symmetric", action="store_true",
+    g = p.add_mutually_exclusive_group()
+    g.add_argument("--reference-compat", action="store_true",
+                   help="(addition, the default) keep the identity matrix exactly as the reference's reporter "
+                        "fills it: only [q][t], q < t")
+    g.add_argument("--symmetric", action="store_true",
                    help="(addition) mirror the identity matrix before clustering instead of keeping the "
                         "reference's upper-triangle-only matrix")
     return p
