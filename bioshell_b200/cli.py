@@ -1,10 +1,11 @@
 """`cluster_sequences` -- the command line of the reference's bin/cluster_sequences.rs:18-74,133-261
 on the batched GPU path:  python -m bioshell_b200.cli <in.fasta> --single-link -c 40
 
-Same positional argument, options, defaults and output files as the reference binary.  Additions: `--device` (which GPU) and `--reference-compat` (the default) / `--symmetric` (mirror the
-identity matrix before clustering; without it the matrix stays exactly as the reference's reporter
-fills it, upper triangle only -- SURVEY.md 3.1 note).  There is no CPU fallback: without a B200 the alignment
-call fails.
+Same positional argument, options, defaults and output files as the reference binary.
+Additions: `--device` (which GPU) and `--reference-compat` (the default) / `--symmetric` (mirror
+the identity matrix before clustering; without it the matrix stays exactly as the reference's
+reporter fills it, upper triangle only -- SURVEY.md 3.1 note).  There is no CPU fallback: without a
+B200 the alignment call fails.
 """
 import argparse
 import logging
