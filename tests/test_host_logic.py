@@ -161,3 +161,29 @@ def test_alignment_path_and_step_types():
     with pytest.raises(ValueError, match="Invalid value for AlignmentStep"):
         bs.AlignmentPath.try_from("**x*")
     assert bs.AlignmentPath.from_attrs([bs.AlignmentStep.Match, bs.AlignmentStep.Vertical]) == "*|"
+
+
+def test_every_entry_point_rejects_a_null_context_without_touching_a_device():
+    """Argument validation only (no compute, no GPU needed): a NULL context is BSA_ERR_BAD_ARG
+    everywhere, never a crash; bsa_destroy(NULL) and bsa_host_free_pinned(NULL) are no-ops."""
+    import ctypes as C
+    L = _lib.lib()
+    null = C.c_void_p(None)
+    bad = L.bsa_set_scoring(null, None, None, -10, -1)
+    assert bad < 0
+    calls = [
+        lambda: L.bsa_load_sequences(null, 0, None, None, 0),
+        lambda: L.bsa_plan_shards(null, 0, 0, None, 1, None),
+        lambda: L.bsa_align_all_pairs(null, 0, 0, None, 0, 0, 3, None, None, None),
+        lambda: L.bsa_all_vs_all(null, 0, 3, None, None),
+        lambda: L.bsa_one_vs_many(null, 0, 1, 1, None, None),
+        lambda: L.bsa_align_pairs_paths(null, 0, 0, None, None, 0, None, None, None, None),
+        lambda: L.bsa_local_align_pairs(null, 0, 0, None, None, 0, None, None, None, None, None, None, None),
+        lambda: L.bsa_hclust(null, 0, None, 0, 0, None, None, None),
+        lambda: L.bsa_get_stats(null, None),
+        lambda: L.bsa_measure_int_peak(null, 0, None, None),
+    ]
+    for call in calls:
+        assert call() == bad
+    L.bsa_destroy(null)
+    L.bsa_host_free_pinned(null)
