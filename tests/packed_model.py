@@ -118,3 +118,30 @@ def tagged_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
         v = Hc[m - 1]
     assert -(1 << 31) <= v < (1 << 31)
     return v >> (cs + xb + 2), v & (U - 1)
+
+
+def wave_ring_schedule(X, WB=32, PF=8, U=2, span=31):
+    """Scalar model of the boundary hand-off of the K3 wavefront consumer (stream_block with WRING,
+    gotoh_kernels.cuh): which boundary entry lane 0 takes at every step and how many entries must
+    have been published when a batch is fetched.  Returns (used, fetches): used[S] = entry index
+    taken at step S (S < X), fetches = [(step, first entry, last entry + 1, needed published)]."""
+    nsteps = (X + span + (U - 1)) // U * U
+    fetches = []
+    ring_cur = {l: l for l in range(WB) if l < X}          # initial batch, waits for min(WB, X)
+    fetches.append((-1, 0, min(WB, X), min(WB, X)))
+    ring_nxt = {}
+    used = {}
+    for s in range(0, nsteps, U):
+        if (s & (WB - 1)) == PF:
+            base = (s & ~(WB - 1)) + WB
+            if base < X:
+                need = min(base + WB, X)
+                ring_nxt = {l: base + l for l in range(WB) if base + l < X}
+                fetches.append((s, base, need, need))
+        for u in range(U):
+            S = s + u
+            if S < X:
+                used[S] = ring_cur.get(S & (WB - 1))
+            if (S & (WB - 1)) == WB - 1:
+                ring_cur = ring_nxt
+    return used, fetches

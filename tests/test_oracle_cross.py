@@ -111,3 +111,21 @@ def test_orientation_matters_for_identity_not_score():
         assert a["score"] == b["score"]
         differ += a["n_identical"] != b["n_identical"]
     assert differ > 0
+
+
+def test_wave_ring_hand_off_schedule_model():
+    """Index logic of the K3 boundary batches (BSA_WAVE_RING; batch 32 is the shipped build, batch 16
+    and later fetch points are prepared switches): lane 0 takes entry S at step S for every row, every
+    batch is fetched before its first use and only needs entries of that batch to be published."""
+    from packed_model import wave_ring_schedule
+    for WB, PFs in ((32, (0, 8, 24, 30)), (16, (0, 8, 14))):
+        for PF in PFs:
+            for X in (1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 100, 1000, 1001):
+                used, fetches = wave_ring_schedule(X, WB, PF)
+                assert used == {S: S for S in range(X)}, (WB, PF, X)
+                for step, first, last, need in fetches:
+                    assert need == last <= X and first % WB == 0
+                    assert step < first                      # fetched before the first step that uses it
+                covered = sorted((f, l) for _, f, l, _ in fetches)
+                assert covered[0][0] == 0 and covered[-1][1] == X
+                assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
