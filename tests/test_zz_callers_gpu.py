@@ -34,3 +34,27 @@ def test_cpp_clustering_mirror_on_gpu(tmp_path):
         r = subprocess.run([CEXE, str(path), "--gpu"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         assert [ln.rstrip() for ln in r.stdout.strip().split("\n")] == [w.rstrip() for w in want]
+
+
+@pytest.mark.gpu
+def test_wavefront_short_queries_against_long_templates(ctx, oracle_matrices):
+    """K3 with queries far shorter than one hand-off batch (1 .. 100 rows) against templates of
+    4,100-6,000 columns: the boundary batches of the wavefront kernel at their edge sizes."""
+    from bioshell_b200 import synth
+    from oracle import c_oracle
+    rng = np.random.default_rng(77)
+    long_res, long_off = synth.generate(3, seed=4242, dist=0, lo=4100, hi=6000)
+    raw_long = long_res.tobytes()
+    shorts = [bytes(rng.choice(list(b"ARNDCQEGHILKMFPSTWYV"), n).astype(np.uint8)) for n in (1, 2, 15, 16, 17, 31, 32, 33, 47, 64, 65, 100)]
+    seqs = [raw_long[int(long_off[i]):int(long_off[i + 1])] for i in range(3)] + shorts
+    res = np.frombuffer(b"".join(seqs), np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
+    ctx.set_scoring("BLOSUM62", -10, -1)
+    ctx.load_sequences(0, res, off)
+    qi = np.array([3 + k for k in range(len(shorts))] * 2)
+    ti = np.array([0] * len(shorts) + [2] * len(shorts))
+    s, nid, paths = ctx.align_pairs_paths(0, 0, qi, ti)
+    M = oracle_matrices["BLOSUM62"]
+    for k in range(len(qi)):
+        one = c_oracle.align_pair(seqs[qi[k]], seqs[ti[k]], M[0], M[1], -10, -1)
+        assert (one["score"], one["n_identical"], one["path"]) == (s[k], nid[k], paths[k].decode()), (qi[k], ti[k])
