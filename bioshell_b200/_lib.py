@@ -17,7 +17,7 @@ ERRORS = {-1: "BAD_ARG", -2: "UNSUPPORTED_GAPS", -3: "RANGE", -4: "CUDA", -5: "O
 WANT_SCORE, WANT_IDENTICAL, OUT_DEVICE, IN_DEVICE = 1, 2, 4, 8
 
 # every symbol include/bioshell_align.h declares
-SYMBOLS = ["bsa_device_count", "bsa_create", "bsa_destroy", "bsa_last_error",
+SYMBOLS = ["bsa_device_count", "bsa_create", "bsa_create_multi", "bsa_context_devices", "bsa_destroy", "bsa_last_error",
            "bsa_parse_ncbi_matrix", "bsa_set_scoring", "bsa_load_sequences", "bsa_align_all_pairs",
            "bsa_all_vs_all", "bsa_one_vs_many", "bsa_plan_shards", "bsa_align_pairs_paths",
            "bsa_host_alloc_pinned", "bsa_host_free_pinned", "bsa_get_stats", "bsa_measure_int_peak",
@@ -56,6 +56,10 @@ def lib():
     L.bsa_device_count.restype = C.c_int
     L.bsa_create.argtypes = [C.c_int]
     L.bsa_create.restype = vp
+    L.bsa_create_multi.argtypes = [vp, C.c_int]
+    L.bsa_create_multi.restype = vp
+    L.bsa_context_devices.argtypes = [vp]
+    L.bsa_context_devices.restype = C.c_int
     L.bsa_destroy.argtypes = [vp]
     L.bsa_destroy.restype = None
     L.bsa_last_error.argtypes = [vp]

@@ -29,14 +29,23 @@ def _p(a):
 
 
 class Context:
-    """One `bsa_ctx`: one CUDA device, one host thread at a time."""
+    """One `bsa_ctx`, used by one host thread at a time.  `device` is a CUDA device index
+    (bsa_create) or a list of them / "all" (bsa_create_multi: one process, every GPU behind the
+    same calls, results streamed tile-wise into the caller's host buffers)."""
 
     def __init__(self, device=0):
         self._L = _lib.lib()
-        self._h = self._L.bsa_create(int(device))
+        if isinstance(device, (list, tuple)) or device == "all":
+            ids = [] if device == "all" else [int(d) for d in device]
+            arr = (C.c_int * max(len(ids), 1))(*ids)
+            self._h = self._L.bsa_create_multi(arr, len(ids))
+            self.device = ids[0] if ids else 0
+        else:
+            self._h = self._L.bsa_create(int(device))
+            self.device = int(device)
         if not self._h:
             raise _lib.BsaError(-4, self._L.bsa_last_error(None).decode())
-        self.device = int(device)
+        self.n_devices = self._L.bsa_context_devices(self._h)
         self._sets = {}
 
     def close(self):

@@ -10,11 +10,17 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gotoh_kernels.cuh"
@@ -76,7 +82,10 @@ struct SeqSet {
 
 }  // namespace
 
+struct MultiState;   // multi_device.inl: the children and worker threads of a multi-device context
+
 struct bsa_ctx {
+    MultiState* multi = nullptr;   // non-null: this context only fans calls out to its children
     int device = 0;
     int sms = 0;
     std::string err;
@@ -159,9 +168,7 @@ struct Reg<0> {
     static void run() {}
 };
 const int kDirsK[] = {2, 4, 8, 12, 16, 24, 32};
-void register_kernels() {
-    static bool done = false;
-    if (done) return;
+void register_kernels_once() {
     Reg<kKStream>::run();
     g_dirs[2] = gotoh_dirs_kernel<2>;
     g_dirs[4] = gotoh_dirs_kernel<4>;
@@ -177,7 +184,10 @@ void register_kernels() {
     g_local[16] = gotoh_local_kernel<16>;
     g_local[24] = gotoh_local_kernel<24>;
     g_local[32] = gotoh_local_kernel<32>;
-    done = true;
+}
+void register_kernels() {
+    static std::once_flag once;
+    std::call_once(once, register_kernels_once);
 }
 // profile + border vectors + the TMA staging area (gotoh_kernels.cuh, smem layout)
 size_t smem_for(int K, int C) { return (size_t)(C + 2) * ((K + 3) / 4) * 32 * sizeof(uint4) + stage_bytes(K, C); }
@@ -313,6 +323,16 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             const int K = wave ? kWaveK : choose_dirs_k(m, C);
             if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
             const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
+            // these kernels hold score * 4 + priority in an int32 (cs = 0): every DP value of the pair,
+            // the borders over the padded columns and one opening below them must stay inside 29 bits
+            {
+                const uint64_t m_pad = npass * 32ull * K;
+                const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min(n, m);
+                const int64_t lb = 4 * (int64_t)(-(int64_t)ctx->go) + (int64_t)(n + m_pad + 4) * (-(int64_t)ctx->ge) +
+                                   (int64_t)std::max(-ctx->min_m, 0);
+                if (std::max(ub, lb) + 8 >= ((int64_t)1 << 29))
+                    return fail(ctx, BSA_ERR_RANGE, "pair too long for these gap penalties / scores: score * 4 leaves int32");
+            }
             const uint64_t words = npass * (n + 32) * 32 * W;
             if (!recs.empty() && (dir_words + words) * 4 > dir_budget) break;
             PairRec pr;
@@ -485,6 +505,8 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
 
 }  // namespace
 
+#include "multi_device.inl"
+
 // =====================================================================
 //                               C ABI
 // =====================================================================
@@ -526,6 +548,7 @@ bsa_ctx* bsa_create(int device_id) {
 
 void bsa_destroy(bsa_ctx* c) {
     if (!c) return;
+    if (c->multi) { multi_destroy(c); return; }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
@@ -605,10 +628,14 @@ int bsa_parse_ncbi_matrix(const char* text, size_t len, int32_t score[441], uint
 int bsa_set_scoring(bsa_ctx* ctx, const int32_t score[441], const uint8_t aa_index[256],
                     int32_t gap_open, int32_t gap_extend) {
     if (!ctx || !score || !aa_index) return fail(ctx, BSA_ERR_BAD_ARG, "null argument");
+    if (ctx->multi) return multi_set_scoring(ctx, score, aa_index, gap_open, gap_extend);
     // outside this domain the reference's sentinel can tie or its backtrace underflows
     // (SURVEY.md 8a note 1); the kernels drop the sentinel, so refuse.
     if (!(gap_open <= gap_extend && gap_extend <= 0 && gap_open < 0))
         return fail(ctx, BSA_ERR_UNSUPPORTED_GAPS, "need gap_open <= gap_extend <= 0 and gap_open < 0");
+    // every kernel multiplies the gap penalties by the lane's score unit (>= 4); larger values could
+    // never pass the per-template range checks anyway
+    if (gap_open < -(1 << 20)) return fail(ctx, BSA_ERR_RANGE, "gap_open below -2^20");
     int mx = -1000000, mn = 1000000;
     for (int i = 0; i < 441; ++i) {
         if (score[i] > 32000 || score[i] < -32000) return fail(ctx, BSA_ERR_RANGE, "substitution score out of int16 range");
@@ -631,6 +658,7 @@ int bsa_set_scoring(bsa_ctx* ctx, const int32_t score[441], const uint8_t aa_ind
 int bsa_load_sequences(bsa_ctx* ctx, int set_id, const uint8_t* residues_raw, const uint64_t* offsets,
                        uint32_t n) {
     if (!ctx) return BSA_ERR_BAD_ARG;
+    if (ctx->multi) return multi_load_sequences(ctx, set_id, residues_raw, offsets, n);
     if (set_id < 0 || set_id >= kMaxSets || !offsets) return fail(ctx, BSA_ERR_BAD_ARG, "bad set_id or null offsets");
     if (n == 0) return fail(ctx, BSA_ERR_EMPTY, "empty sequence set");
     for (uint32_t i = 0; i < n; ++i)
@@ -725,6 +753,8 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                         uint32_t t_end, uint32_t flags, int32_t* scores, uint32_t* n_identical,
                         uint64_t* n_results) {
     if (!ctx) return BSA_ERR_BAD_ARG;
+    if (ctx->multi)
+        return multi_align_all_pairs(ctx, q_set, t_set, q_counts, t_begin, t_end, flags, scores, n_identical, n_results);
     const auto wall0 = std::chrono::steady_clock::now();
     if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets)
         return fail(ctx, BSA_ERR_BAD_ARG, "bad set id");
@@ -849,7 +879,10 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_class + 4) * (int64_t)(-ctx->ge) +
                                (int64_t)std::max(-ctx->min_m, 0);
             if (std::max(ub, lb) + 8 >= lim) continue;
-            const bool tag = use_tag && std::max(ub, lb) + 8 < lim_tag;
+            // TAG cells live in the moving frame score - (i + j) ge: [-(4 |go| + ...), max(M) min(n, m) + (n + m) |ge|]
+            const int64_t ubf = ub + (int64_t)(Q.maxlen + m_class + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+            const int64_t lbf = 4 * (int64_t)(-ctx->go) + 8 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
+            const bool tag = use_tag && std::max(ubf, lbf) + 8 < lim_tag;
             by_k[(m + 15) / 16 + (tag ? kGroupStride : 0)].push_back(t);
         }
         for (int gk = 1; gk < 2 * kGroupStride; ++gk) {
@@ -914,7 +947,10 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
                            (int64_t)std::max(-ctx->min_m, 0);
         const bool fits = std::max(ub, lb) + 8 < lim;
-        const bool fits_tag = use_tag && std::max(ub, lb) + 8 < lim_tag;   // room for the streak field too
+        // TAG cells live in the moving frame score - (i + j) ge: [-(4 |go| + ...), max(M) min(n, m) + (n + m) |ge|]
+        const int64_t ubf = ub + (int64_t)(Q.maxlen + 32ull * kc.K * kc.npass + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+        const int64_t lbf = 4 * (int64_t)(-ctx->go) + 8 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
+        const bool fits_tag = use_tag && std::max(ubf, lbf) + 8 < lim_tag;   // room for the tag field too
         const uint64_t m_pad = 32ull * kc.K * kc.npass;
         uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
         // short templates: keep items small enough that their group still fills the GPU;
@@ -1254,6 +1290,13 @@ int bsa_align_pairs_paths(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
                           uint64_t n_pairs, int32_t* scores, uint32_t* n_identical, uint8_t* path_buf,
                           uint64_t* path_off) {
     if (!ctx) return BSA_ERR_BAD_ARG;
+    if (ctx->multi)
+        return multi_pair_list(ctx, q_set, t_set, q_idx, t_idx, n_pairs, path_buf, path_off,
+                               [&](bsa_ctx* kid, uint64_t a, uint64_t cnt, uint8_t* pb, uint64_t* po) {
+                                   return bsa_align_pairs_paths(kid, q_set, t_set, q_idx + a, t_idx + a, cnt,
+                                                                scores ? scores + a : nullptr,
+                                                                n_identical ? n_identical + a : nullptr, pb, po);
+                               });
     const auto wall0 = std::chrono::steady_clock::now();
     if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets)
         return fail(ctx, BSA_ERR_BAD_ARG, "bad set id");
@@ -1346,6 +1389,14 @@ int bsa_local_align_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
                           uint64_t n_pairs, int32_t* scores, uint32_t* end_q, uint32_t* end_t, uint32_t* start_q,
                           uint32_t* start_t, uint8_t* path_buf, uint64_t* path_off) {
     if (!ctx) return BSA_ERR_BAD_ARG;
+    if (ctx->multi)
+        return multi_pair_list(ctx, q_set, t_set, q_idx, t_idx, n_pairs, path_buf, path_off,
+                               [&](bsa_ctx* kid, uint64_t a, uint64_t cnt, uint8_t* pb, uint64_t* po) {
+                                   return bsa_local_align_pairs(kid, q_set, t_set, q_idx + a, t_idx + a, cnt,
+                                                                scores ? scores + a : nullptr, end_q ? end_q + a : nullptr,
+                                                                end_t ? end_t + a : nullptr, start_q ? start_q + a : nullptr,
+                                                                start_t ? start_t + a : nullptr, pb, po);
+                               });
     const auto wall0 = std::chrono::steady_clock::now();
     if (q_set < 0 || q_set >= kMaxSets || t_set < 0 || t_set >= kMaxSets)
         return fail(ctx, BSA_ERR_BAD_ARG, "bad set id");
@@ -1417,6 +1468,13 @@ int bsa_local_align_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
 int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_t flags, uint32_t* mat_i,
                uint32_t* mat_j, float* merge_dist) {
     if (!ctx) return BSA_ERR_BAD_ARG;
+    if (ctx->multi) {   // the clustering runs on the first device
+        bsa_ctx* kid = ctx->multi->workers[0]->kid;
+        const int rc = bsa_hclust(kid, n, dist, linkage, flags, mat_i, mat_j, merge_dist);
+        ctx->err = kid->err;
+        ctx->stats = kid->stats;
+        return rc;
+    }
     if (n == 0 || !dist || linkage < 0 || linkage > 5) return fail(ctx, BSA_ERR_BAD_ARG, "bad argument");
     const auto wall0 = std::chrono::steady_clock::now();
     CK(cudaSetDevice(ctx->device));
@@ -1544,6 +1602,7 @@ int bsa_get_stats(const bsa_ctx* ctx, bsa_stats* out) {
 
 int bsa_measure_int_peak(bsa_ctx* ctx, int which, double* lane_ops_per_s, double* sm_clock_mhz) {
     if (!ctx || !lane_ops_per_s) return BSA_ERR_BAD_ARG;
+    if (ctx->multi) ctx = ctx->multi->workers[0]->kid;
     CK(cudaSetDevice(ctx->device));
     double ops = 0, mhz = 0;
     cudaError_t e = bsa::measure_int_peak(which, ctx->sms, ctx->streams[0], &ops, &mhz);

@@ -161,23 +161,35 @@ __device__ __forceinline__ int addmax_s32(int a, int b, int c) { return __viaddm
 
 struct Consts {
     int GE, GO, MASK, PH, PV, T_PAD;
-    int GEB;  // border step gap_extend << sh (GE also carries the streak increment in TAG mode)
-    int GOE, GOF;  // TAG: gap_open with the E / F priority already in place (== GO otherwise)
+    int GEB;  // border step gap_extend << sh (0 in TAG mode: the frame makes the borders constant)
+    int GOE, GOF;  // TAG: (gap_open - gap_extend) with the E / F priority already in place (== GO otherwise)
     int XCLR;      // TAG: clears the streak field
-    int hb0;  // packed H[1][0] = gap_open
+    int X1;        // TAG: one unit of the streak field
+    int XTOP;      // TAG: top bit of the streak field ("older than every opening of this block of rows")
+    int TSUB;      // TAG: what the frame adds to every substitution score, in score units (-2 gap_extend)
+    int ge;        // gap_extend (TAG: the emitted score is H* + (n + m) gap_extend)
+    int hb0;  // packed H[1][0] = gap_open   (TAG: H*[i][0] = gap_open - gap_extend for every i >= 1)
     int cs;   // width of the count field
     int ps;   // position of the 2-bit priority field (cs, or cs + kTagBits in TAG mode)
     int sh;   // position of the score field (ps + 2)
     bool local;   // Smith-Waterman borders: everything starts at 0
 };
 
-// TAG cell (score + identity kernels): width of the streak field x that sits between the count
+// TAG cell (score + identity kernels): width of the tag field x that sits between the count
 // and the priority,   v = score << (cs+7) | prio << (cs+5) | x << cs | count.
 // E and F values are born with their H-max priority (2 / 1) already in place, so the two
-// `| PH`, `| PV` of the classic cell disappear; "extend beats open on ties" (global.rs:109,122)
-// comes from x: an extension adds 1 to x, an opening has x = 0.  x only matters in the one
-// comparison that follows the increment, so it is simply cleared when E enters the next lane
-// (<= K <= 20 increments) and every kTagRows rows for F: it never reaches 2^kTagBits.
+// `| PH`, `| PV` of the classic cell disappear.
+// MOVING FRAME (round 2): the score field of DP cell (i, j) holds  score - (i + j) * gap_extend.
+// In that frame BOTH gap extensions are free (E*[j+1] = max(E*[j], H* + go - ge), the same for F
+// down the rows), the diagonal adds (s - 2 ge) -- folded into the profile -- and the borders are
+// the constant go - ge.  "Extend beats open on ties" (global.rs:109,122) comes from x:
+//   E: an extension adds 1 to x and nothing else (the addend of its VIADDMNMX), an opening has
+//      x = 0; x is cleared when E enters the next lane (<= K <= 20 increments);
+//   F: no addition at all -- the OPENING of step s carries x = 15 - (s mod 16), so an older
+//      opening outranks a newer one, and every kTagRows steps the stored F get the top bit of x
+//      (an OR), which outranks every opening of the next 16 steps.
+// The cell is 6 instructions: IMAD (diagonal), VIMNMX3, LOP3, IMAD (E opening), 2 VIADDMNMX.
+// tests/packed_model.py::frame_align is the scalar model of exactly this arithmetic.
 constexpr int kTagBits = 5;
 constexpr uint32_t kTagRows = 16;
 
@@ -309,7 +321,7 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
             int val = cs.T_PAD;
             if (c < K && col < m) {
                 const int tcode = tc[col] & kCodeMask;
-                val = (int)subst[code * C + tcode] * S + P3 +
+                val = ((int)subst[code * C + tcode] + cs.TSUB) * S + P3 +
                       ((cs.cs > 0 && tcode == code && !gap) ? 1 : 0);   // no count field when cs == 0
             }
             o[e] = val;
@@ -317,7 +329,9 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
         prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     // top border: H[0][j] = go + (j-1) ge  (global.rs:81-88); eager F for row 1 =
-    // H[0][j] + go (opened, never extended from the sentinel: global.rs:118-128)
+    // H[0][j] + go (opened, never extended from the sentinel: global.rs:118-128).
+    // TAG (moving frame): both are constants, H*[0][j] = go - ge and F*[1][j] = 2 (go - ge), the
+    // latter with the top tag bit (it is older than every opening that follows)
     for (int r = threadIdx.x; r < ROW; r += blockDim.x) {
         const int v = r >> 5, lane = r & 31;
         int h[4], f[4];
@@ -325,9 +339,9 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
         for (int e = 0; e < 4; ++e) {
             const int c = 4 * v + e;
             const long long j = (long long)colbase + lane * K + c + 1;  // DP column
-            const int hv = cs.local ? 0 : (int)((a.go + (j - 1) * a.ge) * S);
+            const int hv = cs.local ? 0 : (cs.XTOP ? cs.hb0 : (int)((a.go + (j - 1) * a.ge) * S));
             h[e] = hv;
-            f[e] = cs.local ? 0 : hv + cs.GOF;
+            f[e] = cs.local ? 0 : hv + cs.GOF + cs.XTOP;
         }
         rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
         rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -375,20 +389,19 @@ __device__ __forceinline__ void load_vec16(int (&dst)[K], const uint4* __restric
 template <int K, bool DIRS, bool LOCAL = false, bool TAG = false>
 __device__ __forceinline__ void cell_row(const int (&Hold)[K], int (&Hnew)[K], int (&Fr)[K],
                                          const int (&T)[K], int hd, int& er, const Consts& cs,
-                                         const int one, const int one2, uint32_t (&dw)[KTraits<K>::W],
+                                         const int one, const int cf, uint32_t (&dw)[KTraits<K>::W],
                                          int& rowmax) {
     if constexpr (TAG) {
-        // 4 ALU-pipe instructions (VIMNMX3, LOP3, 2 VIADDMNMX) + 3 IMAD; `one` and `one2` are two
-        // separate runtime 1s so that the two openings stay two IMADs (no shared product + IADD3)
+        // the frame cell: 4 ALU-pipe instructions (VIMNMX3, LOP3, 2 VIADDMNMX) + 2 IMAD; `cf` is this
+        // step's F opening addend ((go - ge) << sh | prio 1 | x = 15 - step mod 16)
 #pragma unroll
         for (int c = 0; c < K; ++c) {
             const int d = hd * one + T[c];
             const int h = max3_s32(d, er, Fr[c]);
             const int hc = h & cs.MASK;
             const int hge = hc * one + cs.GOE;
-            const int hgf = hc * one2 + cs.GOF;
-            er = addmax_s32(er, cs.GE, hge);
-            Fr[c] = addmax_s32(Fr[c], cs.GE, hgf);
+            er = addmax_s32(er, cs.X1, hge);
+            Fr[c] = addmax_s32(hc, cf, Fr[c]);
             hd = Hold[c];
             Hnew[c] = hc;
         }
@@ -476,7 +489,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                                              uint32_t* __restrict__ dirs, uint2* scratch_out = nullptr,
                                              const uint32_t* prog_in = nullptr,
                                              uint32_t* prog_out = nullptr, LaneBest* lane_best = nullptr,
-                                             const uint32_t colbase = 0, const int one2 = 1) {
+                                             const uint32_t colbase = 0, const int one2 = 1,
+                                             const int m_emit = 0) {
     static_assert(!TAG || (!DIRS && !LOCAL && !WAVE), "the TAG cell carries no direction bits");
     constexpr int W = KTraits<K>::W;
     constexpr int ROWB = (P16 ? ((K + 7) / 8) * 32 : KTraits<K>::ROW) * (int)sizeof(uint4);
@@ -495,6 +509,8 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
     int hb = cs.hb0;
     int oh = 0, oe = 0;
     uint32_t emitted = 0;
+    uint32_t qstart = 0;   // TAG: stream position at which this lane's current query began (the frame needs its length)
+    int cf = cs.GOF;       // TAG: F opening addend of the current step
     const bool border = !MULTI || first;
     const bool lane0 = lrel == 0;
     const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
@@ -568,13 +584,14 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
         }                                                                                         \
         if (TAG) er &= cs.XCLR;   /* the streak restarts in every lane */                         \
         if (MULTI && !RING && !first && lane0 && (S) + 1 < X) sc_next = scratch[(S) + 1];         \
-        hb += cs.GEB;                                                                             \
+        if (!TAG) hb += cs.GEB;          /* TAG: the frame keeps the left border constant */       \
         const int hd = hdiag;                                                                     \
         hdiag = hin;                                                                              \
         uint32_t dw[W];                                                                           \
         _Pragma("unroll") for (int w = 0; w < W; ++w) dw[w] = 0u;                                 \
         int rowmax = 0;                                                                           \
-        cell_row<K, DIRS, LOCAL, TAG>(HO, HN, Fr, T, hd, er, cs, one, one2, dw, rowmax);                     \
+        cell_row<K, DIRS, LOCAL, TAG>(HO, HN, Fr, T, hd, er, cs, one, TAG ? cf : one2, dw, rowmax); \
+        if (TAG) cf -= cs.X1;            /* the next step's openings rank below this step's */      \
         if (LOCAL && rowmax > lbest.v && (S) - (uint32_t)lane < X) {                              \
             /* a new best in this lane: remember the row and the first column that holds it */   \
             lbest.v = rowmax;                                                                     \
@@ -609,10 +626,12 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                 int v = 0;                                                                        \
                 _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = HN[c];      \
                 const uint64_t k = out_idx0 + emitted;                                            \
-                if (scores) scores[k] = v >> cs.sh;                                               \
+                /* TAG: out of the frame, H = H* + (n + m) ge with n = rows of this query */       \
+                if (scores) scores[k] = (v >> cs.sh) + (TAG ? (int)(pos + 1u - qstart + (uint32_t)m_emit) * cs.ge : 0); \
                 if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                       \
             }                                                                                     \
             emitted += valid ? 1u : 0u;                                                           \
+            qstart = pos + 1u;                                                                    \
             load_vec<K>(HN, rsH + lane);                                                          \
             load_vec<K>(Fr, rsF + lane);                                                          \
             hdiag = hdiag0;                                                                       \
@@ -643,8 +662,10 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             }
         }
         if (TAG && (s & (kTagRows - 1u)) == 0u) {
+            // a new block of 16 steps: what is stored outranks every opening of the block
 #pragma unroll
-            for (int c = 0; c < K; ++c) Fr[c] &= cs.XCLR;
+            for (int c = 0; c < K; ++c) Fr[c] |= cs.XTOP;
+            cf = cs.GOF + (int)(kTagRows - 1u) * cs.X1;
         }
         uint32_t any = 0;
 #pragma unroll
@@ -704,10 +725,10 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
                                                   const int lane, const int lane_last, const int slot_last,
                                                   const int hdiag0, const Consts cs, const int one, const int one2,
                                                   int32_t* __restrict__ scores, uint32_t* __restrict__ nident,
-                                                  uint64_t out_idx0) {
+                                                  uint64_t out_idx0, const int m_emit) {
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
     constexpr int U = BSA_TAG2_U;  // double steps per loop iteration (an even count lets H[] return to its registers)
-    static_assert(8 % U == 0, "the F streak is cleared every 8 double steps");
+    static_assert(8 % U == 0, "the stored F get the top tag bit every 8 double steps");
     const uint32_t X = (uint32_t)(g1 - g0);
     const int span = HALF ? 15 : lane_last;
     const uint32_t nd = ((X + 1u) / 2u + (uint32_t)span + (U - 1)) / U * U;
@@ -717,9 +738,11 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
     int H[K], Fr[K], T0[K], T1[K];
     load_vec<K>(H, rsH + lane);
     load_vec<K>(Fr, rsF + lane);
-    int hdiag = hdiag0, hb = cs.hb0;
+    int hdiag = hdiag0;
+    const int hb = cs.hb0, eb = cs.hb0 + cs.GOE;   // the frame's constant left border: H*[i][0], E*[i][1]
+    int cf = cs.GOF;                               // F opening addend of the first row of the current double step
     int oh0 = 0, oe0 = 0, oh1 = 0, oe1 = 0;
-    uint32_t emitted = 0;
+    uint32_t emitted = 0, qstart = 0;
     const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
     const uint8_t* p = codes + g0 - 2 * lrel;   // lane's first row at double step 0 (may sit in the padding)
     uint32_t b[2 * U], nb[2 * U];
@@ -727,10 +750,9 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
     for (int u = 0; u < 2 * U; ++u) b[u] = ld_code(p + u);
 
     // one row, in place (the checked path)
-#define BSA_ROW1(TT, HIN, ER, OH, OE)                                                             \
+#define BSA_ROW1(TT, HIN, ER, OH, OE, CF)                                                         \
     {                                                                                             \
-        if (lane0) { HIN = hb; ER = hb + cs.GOE; }                                                \
-        hb += cs.GEB;                                                                             \
+        if (lane0) { HIN = hb; ER = eb; }                                                         \
         ER &= cs.XCLR;                                                                            \
         int hd = hdiag;                                                                           \
         hdiag = HIN;                                                                              \
@@ -738,8 +760,8 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
             const int d = hd * one + TT[c];                                                       \
             const int h = max3_s32(d, ER, Fr[c]);                                                 \
             const int hc = h & cs.MASK;                                                           \
-            ER = addmax_s32(ER, cs.GE, hc * one + cs.GOE);                                        \
-            Fr[c] = addmax_s32(Fr[c], cs.GE, hc * one2 + cs.GOF);                                 \
+            ER = addmax_s32(ER, cs.X1, hc * one + cs.GOE);                                        \
+            Fr[c] = addmax_s32(hc, CF, Fr[c]);                                                    \
             hd = H[c];                                                                            \
             H[c] = hc;                                                                            \
         }                                                                                         \
@@ -753,14 +775,15 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
             int v = 0;                                                                            \
             _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = H[c];           \
             const uint64_t k = out_idx0 + emitted;                                                \
-            if (scores) scores[k] = v >> cs.sh;                                                   \
+            /* out of the frame: H = H* + (n + m) ge, n = rows of this query */                   \
+            if (scores) scores[k] = (v >> cs.sh) + (int)((POS) + 1u - qstart + (uint32_t)m_emit) * cs.ge; \
             if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                           \
         }                                                                                         \
         emitted += valid ? 1u : 0u;                                                               \
+        qstart = (POS) + 1u;                                                                      \
         load_vec<K>(H, rsH + lane);                                                               \
         load_vec<K>(Fr, rsF + lane);                                                              \
         hdiag = hdiag0;                                                                           \
-        hb = cs.hb0;                                                                              \
     }
 
     // two rows interleaved, in place (needs: no lane ends a sequence on the FIRST of the two rows)
@@ -768,11 +791,10 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
     {                                                                                             \
         if (lane0) {                                                                              \
             hin0 = hb;                                                                            \
-            er0 = hb + cs.GOE;                                                                    \
-            hin1 = hb + cs.GEB;                                                                   \
-            er1 = hin1 + cs.GOE;                                                                  \
+            er0 = eb;                                                                             \
+            hin1 = hb;                                                                            \
+            er1 = eb;                                                                             \
         }                                                                                         \
-        hb += 2 * cs.GEB;                                                                         \
         er0 &= cs.XCLR;                                                                           \
         er1 &= cs.XCLR;                                                                           \
         int hd0 = hdiag, hd1 = hin0;                                                              \
@@ -783,14 +805,14 @@ _Pragma("unroll")                                                               
             const int d0 = hd0 * one + T0[c];                                                     \
             const int h0 = max3_s32(d0, er0, Fr[c]);                                              \
             const int hc0 = h0 & cs.MASK;                                                         \
-            er0 = addmax_s32(er0, cs.GE, hc0 * one + cs.GOE);                                     \
-            const int f1 = addmax_s32(Fr[c], cs.GE, hc0 * one2 + cs.GOF);                         \
+            er0 = addmax_s32(er0, cs.X1, hc0 * one + cs.GOE);                                     \
+            const int f1 = addmax_s32(hc0, cf0, Fr[c]);                                           \
             hd0 = H[c];                                                                           \
-            const int d1 = hd1 * one + T1[c];                                                     \
+            const int d1 = hd1 * one2 + T1[c];                                                    \
             const int h1 = max3_s32(d1, er1, f1);                                                 \
             hc1 = h1 & cs.MASK;                                                                   \
-            er1 = addmax_s32(er1, cs.GE, hc1 * one + cs.GOE);                                     \
-            Fr[c] = addmax_s32(f1, cs.GE, hc1 * one2 + cs.GOF);                                   \
+            er1 = addmax_s32(er1, cs.X1, hc1 * one2 + cs.GOE);                                    \
+            Fr[c] = addmax_s32(hc1, cf1, f1);                                                     \
             hd1 = hc0;                                                                            \
             H[c] = hc1;                                                                           \
         }                                                                                         \
@@ -802,8 +824,10 @@ _Pragma("unroll")                                                               
 
     for (uint32_t S = 0; S < nd; S += U) {
         if ((S & 7u) == 0u) {
+            // a new block of 16 rows: what is stored outranks every opening of the block
 #pragma unroll
-            for (int c = 0; c < K; ++c) Fr[c] &= cs.XCLR;
+            for (int c = 0; c < K; ++c) Fr[c] |= cs.XTOP;
+            cf = cs.GOF + (int)(kTagRows - 1u) * cs.X1;
         }
         uint32_t any = 0;
 #pragma unroll
@@ -821,6 +845,8 @@ _Pragma("unroll")                                                               
                 int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+                const int cf0 = cf, cf1 = cf - cs.X1;
+                cf -= 2 * cs.X1;
                 BSA_PAIR2()
             }
         } else {
@@ -833,14 +859,16 @@ _Pragma("unroll")                                                               
                 int er0 = __shfl_up_sync(0xffffffffu, oe0, 1);
                 int hin1 = __shfl_up_sync(0xffffffffu, oh1, 1);
                 int er1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+                const int cf0 = cf, cf1 = cf - cs.X1;
+                cf -= 2 * cs.X1;
                 if (BSA_FLAG_SPLIT && !__any_sync(0xffffffffu, BSA_B(u, 0) & kLastFlag)) {
                     // flags only on the second row: the interleaved step stays valid, reset afterwards
                     BSA_PAIR2()
                     BSA_FLAG1(BSA_B(u, 1), pos0 + 1u)
                 } else {
-                    BSA_ROW1(T0, hin0, er0, oh0, oe0)
+                    BSA_ROW1(T0, hin0, er0, oh0, oe0, cf0)
                     BSA_FLAG1(BSA_B(u, 0), pos0)
-                    BSA_ROW1(T1, hin1, er1, oh1, oe1)
+                    BSA_ROW1(T1, hin1, er1, oh1, oe1, cf1)
                     BSA_FLAG1(BSA_B(u, 1), pos0 + 1u)
                 }
                 if (BSA_FLAG_LOOP) {   // rolled loop: the next double step's residues move to b[0], b[1]
@@ -876,20 +904,24 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool l
     cs.sh = cs.ps + 2;
     const int S = 1 << cs.sh;
     const int xmask = tag ? ((1 << kTagBits) - 1) << cshift : 0;
-    cs.GEB = ge * S;
-    cs.GE = ge * S + (tag ? 1 << cshift : 0);
+    cs.GEB = tag ? 0 : ge * S;
+    cs.GE = tag ? 1 << cshift : ge * S;
     cs.GO = go * S;
     cs.MASK = ~((3 << cs.ps) | xmask);
     cs.XCLR = ~xmask;
+    cs.X1 = 1 << cshift;
+    cs.XTOP = tag ? 1 << (cshift + kTagBits - 1) : 0;
+    cs.TSUB = tag ? -2 * ge : 0;
+    cs.ge = ge;
     cs.PH = 2 << cs.ps;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
     cs.PV = 1 << cs.ps;   // F: vertical, gap in the template
-    cs.GOE = cs.GO + (tag ? cs.PH : 0);
-    cs.GOF = cs.GO + (tag ? cs.PV : 0);
+    cs.GOE = tag ? (go - ge) * S + cs.PH : cs.GO;
+    cs.GOF = tag ? (go - ge) * S + cs.PV : cs.GO;
     // padded columns: neutral in global mode; in local mode they must never score, so that no
     // cell outside the template can reach the best score (anything they inherit through E/F is
     // strictly below a real cell of the same row)
     cs.T_PAD = local ? -(1 << 24) : 3 << cs.ps;
-    cs.hb0 = go * S;
+    cs.hb0 = tag ? (go - ge) * S : go * S;
     cs.local = local;
     return cs;
 }
@@ -961,7 +993,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
             const int lane_last = (int)((m - 1 - colbase) / K);
             const int slot_last = (int)((m - 1 - colbase) % K);
             const long long jl = (long long)colbase + (long long)lane * K;  // DP column left of the lane
-            const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * (1 << cs.sh));
+            const int hdiag0 = jl == 0 ? 0 : (TAG ? cs.hb0 : (int)((a.go + (jl - 1) * a.ge) * (1 << cs.sh)));
             for (;;) {
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(&s_chunk, 1u);
@@ -979,12 +1011,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
                 if constexpr (TAG && !MULTI && TwoRows<K, false>::value)
                     stream_block_tag2<K, false>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, lane_last, slot_last,
                                                 hdiag0, cs, a.one, a.one2, a.scores, a.nident,
-                                                it.out_base + (qa - it.q_begin));
+                                                it.out_base + (qa - it.q_begin), (int)m);
                 else
                     stream_block<K, false, MULTI, false, false, false, TAG>(
                         a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp, lastp ? lane_last : 31,
                         slot_last, hdiag0, cs, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores, a.nident,
-                        it.out_base + (qa - it.q_begin), nullptr, nullptr, nullptr, nullptr, nullptr, 0, a.one2);
+                        it.out_base + (qa - it.q_begin), nullptr, nullptr, nullptr, nullptr, nullptr, 0, a.one2, (int)m);
             }
         }
     }
@@ -1457,7 +1489,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
                 int val = cs.T_PAD;
                 if (c < K && col < m) {
                     const int tcode = tc[col] & kCodeMask;
-                    val = (int)s_subst[code * a.C + tcode] * S + P3 + ((tcode == code && !gap) ? 1 : 0);
+                    val = ((int)s_subst[code * a.C + tcode] + cs.TSUB) * S + P3 + ((tcode == code && !gap) ? 1 : 0);
                 }
                 o[e] = val;
             }
@@ -1469,8 +1501,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const long long j = (long long)(ln & 15) * K + 4 * v + e + 1;
-                h[e] = (int)((a.go + (j - 1) * a.ge) * S);
-                f[e] = h[e] + cs.GOF;
+                h[e] = TAG ? cs.hb0 : (int)((a.go + (j - 1) * a.ge) * S);   // TAG: constant borders of the frame
+                f[e] = h[e] + cs.GOF + cs.XTOP;
             }
             rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
             rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -1482,7 +1514,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const int my_last = (isB && !hasB) ? -1 : (int)((mine - 1) / K) + (isB ? 16 : 0);
         const int my_slot = mine ? (int)((mine - 1) % K) : 0;
         const long long jl = (long long)lrel * K;
-        const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * S);
+        const int hdiag0 = jl == 0 ? 0 : (TAG ? cs.hb0 : (int)((a.go + (jl - 1) * a.ge) * S));
         for (;;) {
             uint32_t c = 0;
             if (lane == 0) c = atomicAdd(&s_chunk, 1u);
@@ -1497,12 +1529,12 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             if constexpr (TAG && TwoRows<K, true>::value)
                 stream_block_tag2<K, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, my_last, my_slot, hdiag0, cs,
                                            a.one, a.one2, a.scores, a.nident,
-                                           (isB ? it.outB : it.outA) + (qa - it.q_begin));
+                                           (isB ? it.outB : it.outA) + (qa - it.q_begin), (int)mine);
             else
                 stream_block<K, false, false, false, false, true, TAG>(
                     a.Q.codes, g0, g1, prof, rsH, rsF, lane, true, true, my_last, my_slot, hdiag0, cs, a.one, nullptr,
                     a.scores, a.nident, (isB ? it.outB : it.outA) + (qa - it.q_begin), nullptr, nullptr, nullptr,
-                    nullptr, nullptr, 0, a.one2);
+                    nullptr, nullptr, 0, a.one2, (int)mine);
         }
     }
 }

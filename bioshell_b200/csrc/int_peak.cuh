@@ -52,6 +52,14 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int on
                 a[i] = __viaddmax_s32(a[i], ge, hc * one + go);
                 b[i] = __viaddmax_s32(b[i], ge, hc * one2 + ph);
                 c[i] = hc;
+            } else if (WHICH == 8) {
+                // the FRAME cell (TAG mode since round 2): VIMNMX3 + LOP3 + 2 VIADDMNMX (ALU pipe) + 2 IMAD
+                const int d = c[i] * one + ge;
+                const int h = __vimax3_s32(d, a[i], b[i]);
+                const int hc = h & mask;
+                a[i] = __viaddmax_s32(a[i], ge, hc * one2 + go);
+                b[i] = __viaddmax_s32(hc, ph, b[i]);
+                c[i] = hc;
             } else if (WHICH == 1) {
                 a[i] = __viaddmax_s32(a[i], ge, b[i]);
             } else if (WHICH == 2) {
@@ -84,6 +92,7 @@ inline int peak_ops_per_iter(int which) {
     switch (which) {
         case 0: return 8;
         case 7: return 7;
+        case 8: return 6;
         case 2: return 2;   // VIMNMX3 + the LOP3 that perturbs it
         default: return 1;
     }
@@ -110,6 +119,7 @@ inline cudaError_t measure_int_peak(int which, int sms, cudaStream_t st, double*
             case 4: int_peak_kernel<4><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             case 5: int_peak_kernel<5><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             case 7: int_peak_kernel<7><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 8: int_peak_kernel<8><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
         }
     };

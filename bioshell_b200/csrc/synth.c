@@ -112,3 +112,62 @@ uint64_t bsa_synth_generate(uint64_t seed, uint32_t n, int dist, uint32_t lo, ui
     free(buf); free(o); free(tmp);
     return used;
 }
+
+/*
+ * BASELINE configs[4]: n_pairs titin-scale pairs.  Sequence 2p is the
+ * query of pair p, sequence 2p+1 its template; lengths ~ U{lo..hi}.  Even pairs are HOMOLOG
+ * pairs (the query is a mutated copy of the template: substitutions at rate U[0.05,0.6],
+ * indels at 2 %/site, geometric lengths of mean 3), odd pairs are unrelated.  Pair 0 is forced
+ * to fixed_q x fixed_t residues (34,350 x 35,000: titin against a 35,000-residue template)
+ * when fixed_t != 0: the mutated copy is cut, or extended with random residues, to fixed_q.
+ * Same two-call protocol as bsa_synth_generate.
+ */
+uint64_t bsa_synth_pair_set(uint64_t seed, uint32_t n_pairs, uint32_t lo, uint32_t hi, uint32_t fixed_q,
+                            uint32_t fixed_t, uint8_t *res, uint64_t *off) {
+    double cum[20], tot = 0.0;
+    for (int i = 0; i < 20; ++i) tot += FREQ[i];
+    double acc = 0.0;
+    for (int i = 0; i < 20; ++i) { acc += FREQ[i] / tot; cum[i] = acc; }
+    uint32_t cap = (hi > fixed_t ? hi : fixed_t);
+    if (fixed_q > cap) cap = fixed_q;
+    uint8_t *tq = (uint8_t *)malloc((size_t)cap + 64), *tt = (uint8_t *)malloc((size_t)cap + 64);
+    if (!tq || !tt) { free(tq); free(tt); return 0; }
+    uint64_t used = 0;
+    if (off) off[0] = 0;
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        uint64_t st = seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)p + 1) * 0xD1B54A32D192ED03ULL;
+        uint32_t lt = lo + (uint32_t)(u01(&st) * (double)(hi - lo + 1));
+        uint32_t lq = lo + (uint32_t)(u01(&st) * (double)(hi - lo + 1));
+        if (lt > hi) lt = hi;
+        if (lq > hi) lq = hi;
+        const int fixed = (p == 0 && fixed_t != 0);
+        if (fixed) { lt = fixed_t; lq = fixed_q; }
+        for (uint32_t x = 0; x < lt; ++x) tt[x] = draw_residue(&st, cum);
+        uint32_t outl = 0;
+        if ((p & 1u) == 0) {
+            const uint32_t lim = fixed ? lq : cap;
+            double rate = 0.05 + 0.55 * u01(&st);
+            uint32_t k = 0;
+            while (k < lt && outl < lim) {
+                double u = u01(&st);
+                if (u < 0.01) {
+                    k += geometric(&st, 3.0);
+                } else if (u < 0.02) {
+                    uint32_t g = geometric(&st, 3.0);
+                    for (uint32_t x = 0; x < g && outl < lim; ++x) tq[outl++] = draw_residue(&st, cum);
+                } else {
+                    tq[outl++] = (u01(&st) < rate) ? draw_residue(&st, cum) : tt[k];
+                    ++k;
+                }
+            }
+            while (outl < (fixed ? lq : lo)) tq[outl++] = draw_residue(&st, cum);
+        } else {
+            for (uint32_t x = 0; x < lq; ++x) tq[outl++] = draw_residue(&st, cum);
+        }
+        if (res) { memcpy(res + used, tq, outl); memcpy(res + used + outl, tt, lt); }
+        if (off) { off[2 * p + 1] = used + outl; off[2 * p + 2] = used + outl + lt; }
+        used += (uint64_t)outl + lt;
+    }
+    free(tq); free(tt);
+    return used;
+}

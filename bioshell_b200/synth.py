@@ -17,7 +17,9 @@ CONFIGS = {
     "cfg3": dict(n=100000, dist=1, lo=30, hi=4000, mu=5.45, sigma=0.65, seed=1003),
     "cfg4q": dict(n=1000, dist=1, lo=30, hi=4000, mu=5.45, sigma=0.65, seed=1004),
     "cfg4db": dict(n=1000000, dist=1, lo=30, hi=4000, mu=5.45, sigma=0.65, seed=1005),
-    "cfg5": dict(n=32, dist=0, lo=5000, hi=35000, seed=1006),
+    # cfg5 is a PAIR set (see pair_set): 16 pairs, sequence 2p = query, 2p+1 = template of pair p,
+    # lengths U{5000..35000}, even pairs homologous, pair 0 forced to 34,350 x 35,000 residues
+    "cfg5": dict(pairs=16, lo=5000, hi=35000, fixed_q=34350, fixed_t=35000, seed=1006),
 }
 
 
@@ -36,6 +38,9 @@ def _load():
         _lib.bsa_synth_generate.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
                                             C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         _lib.bsa_synth_generate.restype = C.c_uint64
+        _lib.bsa_synth_pair_set.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.bsa_synth_pair_set.restype = C.c_uint64
     return _lib
 
 
@@ -51,8 +56,24 @@ def generate(n, seed, dist=1, lo=30, hi=4000, mu=5.45, sigma=0.65, homolog_fract
     return res[:int(total)], off
 
 
+def pair_set(pairs, seed, lo=5000, hi=35000, fixed_q=0, fixed_t=0):
+    """BASELINE configs[4]: `pairs` (query, template) pairs as 2*pairs sequences -> (residues, offsets).
+    Pair p is (sequence 2p, sequence 2p+1); even pairs are homologous, pair 0 has the fixed lengths."""
+    L = _load()
+    off = np.zeros(2 * pairs + 1, np.uint64)
+    total = L.bsa_synth_pair_set(seed, pairs, lo, hi, fixed_q, fixed_t, None, off.ctypes.data_as(C.c_void_p))
+    res = np.zeros(max(int(total), 1), np.uint8)
+    L.bsa_synth_pair_set(seed, pairs, lo, hi, fixed_q, fixed_t, res.ctypes.data_as(C.c_void_p),
+                         off.ctypes.data_as(C.c_void_p))
+    return res[:int(total)], off
+
+
 def config(name, n=None):
     c = dict(CONFIGS[name])
+    if "pairs" in c:
+        if n is not None:
+            c["pairs"] = n
+        return pair_set(**c)
     if n is not None:
         c["n"] = n
     return generate(**c)

@@ -36,8 +36,9 @@
  * and output buffer and keeps it alive for the duration of the call; the library
  * owns device memory and streams inside bsa_ctx and never retains caller pointers
  * after return.  Calls are synchronous (results complete on return).  A bsa_ctx is
- * bound to ONE CUDA device and used by one host thread at a time; use one context
- * (one process) per GPU and shard by template range for multi-GPU.  There is NO CPU
+ * used by one host thread at a time.  bsa_create binds it to ONE CUDA device (one process per
+ * GPU, sharded by template range with bsa_plan_shards); bsa_create_multi gives a single process
+ * all GPUs behind the same calls.  There is NO CPU
  * fallback: without a usable CUDA device every compute entry point returns
  * BSA_ERR_CUDA.  No C++ exception crosses this boundary.
  */
@@ -77,6 +78,22 @@ int bsa_device_count(void);
 
 /* Create a context on CUDA device `device_id`.  NULL on failure (no device). */
 bsa_ctx *bsa_create(int device_id);
+/*
+ * ONE context over n_dev GPUs for a single-process caller (the reference's caller is one process:
+ * bin/cluster_sequences.rs:173-177 calls align_all_pairs once).  n_dev == 0 takes
+ * every visible device.  Every entry point below behaves as on a single-device context and
+ * returns the same bytes: sequence sets and scoring are replicated to all devices; the library
+ * runs one host worker thread per child context (two per GPU), cuts bsa_align_all_pairs /
+ * bsa_all_vs_all / bsa_one_vs_many into cell-balanced template-range tiles that the workers pull
+ * from a shared counter, and each tile's results are copied by its GPU straight into the caller's
+ * output buffers at the tile's own t-major offset (true DMA, overlapped with the other child's
+ * kernels, when the buffers come from bsa_host_alloc_pinned).  No collective, no NCCL.
+ * Pair-list calls are split into contiguous chunks of equal cells.  BSA_OUT_DEVICE is refused.
+ * bsa_hclust and bsa_measure_int_peak run on the first device.
+ */
+bsa_ctx *bsa_create_multi(const int *device_ids, int n_dev);
+/* Number of GPUs behind this context (1 for bsa_create). */
+int bsa_context_devices(const bsa_ctx *ctx);
 void bsa_destroy(bsa_ctx *ctx);
 
 /* Message of the last error on this context ("" if none). ctx may be NULL for creation errors. */

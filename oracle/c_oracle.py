@@ -32,10 +32,31 @@ def build(force=False):
     return _SO
 
 
+def use_native():
+    """bench.py only: rebuild the oracle with -O3 -march=native for THIS host's CPU (BASELINE.md section 3
+    promises that for the timed CPU baseline) into oracle/_ref/libbioshell_oracle_native.so and bind
+    that from now on.  The portable build stays what the tests use (it travels to the GPU box, whose
+    CPU may differ from the build container's).  Falls back to the portable build if gcc fails."""
+    global _SO, _lib
+    native = os.path.join(_HERE, "_ref", "libbioshell_oracle_native.so")
+    if _SO == native:
+        return True
+    try:
+        os.makedirs(os.path.dirname(native), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fPIC", "-std=c11", "-shared", "-o", native] +
+                              [os.path.join(_HERE, f) for f in ("bioshell_oracle.c", "hclust_oracle.c", "local_oracle.c")] +
+                              ["-lpthread"], stderr=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        return False
+    _SO, _lib = native, None
+    return True
+
+
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if not _SO.endswith("_native.so"):
+            build()
         L = C.CDLL(_SO)
         L.orc_parse_ncbi.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.orc_parse_ncbi.restype = C.c_int

@@ -120,6 +120,65 @@ def tagged_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
     return v >> (cs + xb + 2), v & (U - 1)
 
 
+def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
+    """Model of the FRAME cell (gotoh_kernels.cuh, TAG mode since round 2): the TAG cell in a moving
+    frame.  Every stored DP value of cell (i, j) carries score - (i + j) * ge, so that BOTH gap
+    extensions cost nothing in the frame:
+        D* = H*[i-1][j-1] + (s - 2 ge)         E*[j+1] = max(E*[j], H* + go - ge)      F*[i+1] = max(F*[i], H* + go - ge)
+    and the borders become the constant go - ge.  Extend-beats-open (global.rs:109,122):
+      * E keeps the streak field: the extension adds 1 to x (and nothing to the score), openings have x = 0;
+        x is cleared when E enters the next lane (every K columns).
+      * F needs no addition at all: the OPENING candidate of row i carries x = R-1 - (i mod R), so an
+        older opening outranks a newer one on ties; every R rows the stored F values get the top bit of x
+        (an OR), which outranks every candidate of the next R rows.
+    6 instructions per cell: IMAD (diagonal), VIMNMX3, LOP3, IMAD (E opening), 2 VIADDMNMX."""
+    n, m = len(q), len(t)
+    assert R & (R - 1) == 0 and R <= 1 << (xb - 1)
+    U, X1 = 1 << cs, 1 << cs
+    P1 = 1 << (cs + xb)
+    S = 1 << (cs + xb + 2)
+    XMASK = ((1 << xb) - 1) << cs
+    MASK = ~(3 * P1 | XMASK)
+    XTOP = (1 << (xb - 1)) * X1
+    GOE = (go - ge) * S + 2 * P1
+    GOF = (go - ge) * S + P1
+    HB = (go - ge) * S                      # H*[0][j], j >= 1, and H*[i][0], i >= 1
+    gaps = (ord("-"), ord("_"))
+
+    def T(a, b):
+        ident = 1 if (cs > 0 and a == b and a not in gaps) else 0
+        return (score[aa[a] * 21 + aa[b]] - 2 * ge) * S + 3 * P1 + ident
+
+    Hc = [HB] * m
+    Fr = [HB + GOF + XTOP] * m             # eager F of row 1: opened from the top border, older than any candidate
+    lo, hi = 0, 0
+    for i in range(n):
+        if i % R == 0:
+            Fr = [f | XTOP for f in Fr]
+        cF = GOF + (R - 1 - i % R) * X1
+        er = HB + GOE
+        hd = 0 if i == 0 else HB
+        for c in range(m):
+            if c % K == 0:
+                er &= ~XMASK                      # lane boundary: after the shuffle
+            d = hd + T(q[i], t[c])
+            h = max(d, er, Fr[c])
+            hc = h & MASK
+            er = max(er + X1, hc + GOE)
+            Fr[c] = max(hc + cF, Fr[c])
+            assert (er & XMASK) >> cs <= K
+            assert (er >> (cs + xb)) & 3 == 2 and (Fr[c] >> (cs + xb)) & 3 == 1
+            lo, hi = min(lo, d, er, Fr[c]), max(hi, d, er, Fr[c])
+            hd, Hc[c] = Hc[c], hc
+    assert -(1 << 31) <= lo and hi < (1 << 31)
+    if m == 0:
+        return (0 if n == 0 else go + (n - 1) * ge), 0
+    if n == 0:
+        return go + (m - 1) * ge, 0
+    v = Hc[m - 1]
+    return (v >> (cs + xb + 2)) + (n + m) * ge, v & (U - 1)
+
+
 def wave_ring_schedule(X, WB=32, PF=8, U=2, span=31):
     """Scalar model of the boundary hand-off of the K3 wavefront consumer (stream_block with WRING,
     gotoh_kernels.cuh): which boundary entry lane 0 takes at every step and how many entries must

@@ -7,7 +7,7 @@ import pytest
 
 from bioshell_b200.scoring import ncbi_text
 from oracle import c_oracle, pyoracle
-from packed_model import packed_align, tagged_align, walk_dirs
+from packed_model import frame_align, packed_align, tagged_align, walk_dirs
 
 AA = b"ARNDCQEGHILKMFPSTWYV"
 DIRTY = b"ARNDCQEGHILKMFPSTWYVXBZJUO*-_arndx"
@@ -97,6 +97,27 @@ def test_tagged_lane_model_matches_oracle(alphabet):
         cs = max(len(q), len(t)).bit_length()
         for K, R, xb in ((4, 16, 5), (1, 1, 1), (20, 16, 5), (3, 5, 3)):
             s, nid = tagged_align(q, t, psc, pai, go, ge, cs, xb=xb, K=K, R=R)
+            assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R)
+
+
+@pytest.mark.parametrize("alphabet", [AA, DIRTY])
+def test_frame_lane_model_matches_oracle(alphabet):
+    """The FRAME cell (TAG cell in the moving frame score - (i+j) ge: 4 ALU + 2 IMAD, both extensions free,
+    F tie rule through decreasing candidate tags) gives the reference's score and n_identical for every
+    lane width and clearing period."""
+    text = ncbi_text("BLOSUM62")
+    sc, ai = c_oracle.parse_ncbi(text)
+    psc, pai = pyoracle.parse_ncbi(text)
+    k = 0
+    for q, t in pairs(31, 500, 56, alphabet):
+        go, ge = GAPS[k % len(GAPS)]
+        k += 1
+        if ge == 0 and max(len(q), len(t)) < 2:
+            continue
+        ref = c_oracle.align_pair(q, t, sc, ai, go, ge, max(len(q), len(t)) + 100 * (k % 3))
+        cs = max(len(q), len(t)).bit_length()
+        for K, R, xb in ((4, 16, 5), (1, 1, 1), (20, 16, 5), (3, 4, 3), (7, 2, 5)):
+            s, nid = frame_align(q, t, psc, pai, go, ge, cs, xb=xb, K=K, R=R)
             assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R)
 
 

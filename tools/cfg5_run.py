@@ -14,12 +14,10 @@ from bioshell_b200 import Context, synth  # noqa: E402
 from bioshell_b200.scoring import ncbi_text  # noqa: E402
 from oracle import c_oracle  # noqa: E402
 
-res, off = synth.config("cfg5")                      # 32 sequences, U{5000..35000}, half of them homologs
+res, off = synth.config("cfg5")      # 16 pairs (2p, 2p+1), U{5000..35000}, even pairs homologous, pair 0 = 34,350 x 35,000
 lens = np.diff(off.astype(np.int64))
-order = np.argsort(-lens)
 q = np.arange(0, 32, 2)
 t = np.arange(1, 32, 2)
-q[0], t[0] = order[1], order[0]                      # the two longest sequences as one pair
 with Context(0) as ctx:
     ctx.set_scoring("BLOSUM62", -10, -1)
     ctx.load_sequences(0, res, off)
@@ -31,7 +29,7 @@ with Context(0) as ctx:
 raw = res.tobytes()
 sc, ai = c_oracle.parse_ncbi(ncbi_text("BLOSUM62"))
 checked = []
-for k in (() if os.environ.get("BSA_CFG5_NOCHECK") else (0, 3)):      # NOCHECK: timing only (A/B runs)
+for k in (() if os.environ.get("BSA_CFG5_NOCHECK") else (0, 1)):      # NOCHECK: timing only (A/B runs)
     a = raw[int(off[q[k]]):int(off[q[k] + 1])]
     b = raw[int(off[t[k]]):int(off[t[k] + 1])]
     t0 = time.perf_counter()
