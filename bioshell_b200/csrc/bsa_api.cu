@@ -108,7 +108,8 @@ struct bsa_ctx {
     SeqSet sets[kMaxSets];
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
-        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair;
+        raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair,
+        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC;
     bsa_stats stats;
     uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
 };
@@ -554,7 +555,8 @@ void bsa_destroy(bsa_ctx* c) {
     for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
-                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair};
+                      &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair,
+                      &c->lt_codes, &c->lt_off, &c->lt_idx, &c->lq_codes, &c->lq_off, &c->lq_idx, &c->lutB, &c->lutC};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -789,7 +791,6 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
 
     const double target_cells = std::min(std::max(total_cells / 40000.0, 1048576.0), 268435456.0);
     struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0, swept = 0; };
-    std::vector<Group> groups(4 * kGroupStride);
     const bool use_tag = !getenv("BSA_NO_TAG");
     std::vector<Fix> fixes;
     std::vector<PairReq> fallback;
@@ -858,151 +859,302 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         }
     }
 
-    // ---- short templates: two per warp on 16 lanes each (gotoh_pair_kernel) ----
+    // =====================================================================================
+    // 32-bit lanes (score + identity, and score-only templates the 16-bit lanes cannot take).
+    //
+    // The streaming kernels keep ONE sequence -- the OWNER -- in registers as DP columns and stream
+    // the others through the lanes as rows.  Whoever owns the columns, the pair (q, t) yields the
+    // same result as long as the tie priorities follow the reference's orientation (rows = query):
+    // with the roles swapped, E and F trade their H-max priorities (`flip`).  Three variants:
+    //   A  owner = template t, stream = the query set                         (the reference's layout)
+    //   B  owner = a SHORT query q, stream = the LONG templates with q_counts[t] > q, flipped:
+    //      a template of more than one column block (> 32 x 20 columns) would sweep every query in
+    //      several passes at ~70 % of the single-pass rate; as a ROW stream it costs nothing extra
+    //   C  owner = a long template, stream = the LONG queries only (long x long, what is left)
+    // B and C stream from derived stores that hold only the long sequences (gathered on the
+    // device, original order kept), and scatter their results through a per-stream-sequence table:
+    // k = item.out_base + lut[stream index].  B needs q_counts to be non-decreasing (a suffix of the
+    // long templates per query); otherwise everything stays in A.
+    // =====================================================================================
     struct GroupPair { std::vector<Item16> items; double cells = 0, swept = 0; };
-    std::vector<GroupPair> groups_pair(2 * kGroupStride);   // K + tag * kGroupStride
-    std::vector<uint32_t> qstart((size_t)(t_end - t_begin), 0);   // the one-template path starts here
-    if (Q.empties.empty() && !getenv("BSA_NO_PAIR")) {
-        std::vector<std::vector<uint32_t>> by_k(2 * kGroupStride);
-        for (uint32_t t = t_begin; t < t_end; ++t) {
-            const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
-            const uint64_t m = T.len(t);
-            if (cnt == 0 || m == 0 || m > 16ull * kKStream || done16[t - t_begin]) continue;
-            if (smem_for((int)((m + 15) / 16), C) > kSmemBudget) continue;
-            // the kernel sizes the count field for the longer template of a pair: check with the
-            // widest field any template of this columns-per-lane class can meet
-            const uint64_t m_class = 16ull * ((m + 15) / 16);
-            const int cs = std::min(bitlen(m_class), cs_cap);
-            const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
-            const int64_t lim_tag = cs + kTagBits <= 27 ? (int64_t)1 << (29 - cs - kTagBits) : 0;
-            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_class, Q.maxlen);
-            const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_class + 4) * (int64_t)(-ctx->ge) +
-                               (int64_t)std::max(-ctx->min_m, 0);
-            if (std::max(ub, lb) + 8 >= lim) continue;
-            // TAG cells live in the moving frame score - (i + j) ge: [-(4 |go| + ...), max(M) min(n, m) + (n + m) |ge|]
-            const int64_t ubf = ub + (int64_t)(Q.maxlen + m_class + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
-            const int64_t lbf = 4 * (int64_t)(-ctx->go) + 8 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
-            const bool tag = use_tag && std::max(ubf, lbf) + 8 < lim_tag;
-            by_k[(m + 15) / 16 + (tag ? kGroupStride : 0)].push_back(t);
-        }
-        for (int gk = 1; gk < 2 * kGroupStride; ++gk) {
-            const int K = gk % kGroupStride;
-            if (K < 1 || K > kKStream) continue;
-            const auto& v = by_k[gk];
-            for (size_t i = 0; i + 1 < v.size(); i += 2) {
-                const uint32_t tA = v[i], tB = v[i + 1];
-                const uint32_t cA = q_counts ? q_counts[tA] : Q.n, cB = q_counts ? q_counts[tB] : Q.n;
-                const uint32_t common = std::min(cA, cB);
-                const uint64_t m_pad = 32ull * K;
-                uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
-                xb = std::min<uint64_t>(xb, 1u << 18);
-                uint32_t q = 0;
-                while (q < common) {
-                    const uint64_t lim_off = Q.off[q] + xb;
-                    uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + common + 1, lim_off) -
-                                             Q.off.begin()) - 1;
-                    q2 = std::min(std::max(q2, q + 1), common);
-                    Item16 it;
-                    it.tA = tA; it.tB = tB; it.q_begin = q; it.q_end = q2;
-                    it.outA = first[tA - t_begin] + q;
-                    it.outB = first[tB - t_begin] + q;
-                    groups_pair[gk].items.push_back(it);
-                    const uint64_t x = Q.off[q2] - Q.off[q];
-                    const double sw = (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
-                    padded += sw;
-                    groups_pair[gk].swept += sw;
-                    groups_pair[gk].cells += (double)x * (double)(T.len(tA) + T.len(tB));
-                    q = q2;
-                }
-                qstart[tA - t_begin] = common;     // what is left of the longer query list goes the usual way
-                qstart[tB - t_begin] = common;
+    struct Variant {
+        std::vector<Group> groups;          // K + multi * stride + tag * 2 stride
+        std::vector<GroupPair> pairs;       // K + tag * stride
+        const std::vector<uint64_t>* xoff = nullptr;   // offsets of the stream set (host copy)
+        uint64_t xmax = 0;                  // its longest sequence
+        int cs_cap = 0;                     // count-field cap: bitlen(xmax)
+        SeqStoreDev qdev, tdev;             // stream / owner store on the device
+        const uint64_t* lut = nullptr;      // device: result-index contribution per stream sequence
+        int flip = 0;
+        const char* name = "A";
+    };
+    Variant var[3];
+    for (auto& V : var) { V.groups.resize(4 * kGroupStride); V.pairs.resize(2 * kGroupStride); }
+    var[0].xoff = &Q.off; var[0].xmax = Q.maxlen; var[0].cs_cap = cs_cap;
+    var[0].qdev = Q.dev(); var[0].tdev = T.dev();
+    var[1].name = "B"; var[1].flip = 1;
+    var[2].name = "C";
+
+    const int kc_eff = std::min(k_cap(C), kKStream);
+    const uint64_t Lc = 32ull * (uint64_t)std::max(kc_eff, 1);      // longest single-pass owner
+    auto count_of = [&](uint32_t t) { return q_counts ? q_counts[t] : Q.n; };
+
+    // ---- which templates leave variant A? ----
+    std::vector<uint32_t> lt, lq;            // original indices of the long templates / long queries
+    std::vector<uint64_t> ltoff, lqoff;      // offsets of the two derived stores
+    std::vector<uint8_t> in_lt((size_t)(t_end - t_begin), 0);
+    {
+        bool hybrid = Q.empties.empty() && kc_eff >= 1 && !getenv("BSA_NO_HYBRID");
+        for (uint32_t t = t_begin; hybrid && t + 1 < t_end; ++t)
+            if (count_of(t + 1) < count_of(t)) hybrid = false;      // B needs a suffix per query
+        if (hybrid) {
+            for (uint32_t t = t_begin; t < t_end; ++t)
+                if (T.len(t) > Lc && count_of(t) > 0 && !done16[t - t_begin]) lt.push_back(t);
+            if (!lt.empty()) {
+                const uint32_t max_cnt = count_of(lt.back());
+                for (uint32_t q = 0; q < max_cnt; ++q)
+                    if (Q.len(q) > Lc) lq.push_back(q);
+                for (uint32_t t : lt) in_lt[t - t_begin] = 1;
             }
         }
     }
-
-    for (uint32_t t = t_begin; t < t_end; ++t) {
-        const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
-        if (cnt == 0) continue;
-        if (done16[t - t_begin]) continue;
-        if (qstart[t - t_begin] >= cnt) continue;
-        const uint64_t m = T.len(t);
-        const uint64_t kbase = first[t - t_begin];
-        if (m == 0) {
-            // empty template: the reference returns the row-0 border value... for an empty
-            // query against it the loop never runs: H[0]=0 (global.rs:76,143); otherwise
-            // the left border go + (n-1) ge after n rows (global.rs:99,140).
-            for (uint32_t q = 0; q < cnt; ++q) {
-                const uint64_t n = Q.len(q);
-                fixes.push_back(Fix{kbase + q, n == 0 ? 0 : (int32_t)(ctx->go + (int64_t)(n - 1) * ctx->ge), 0u});
+    std::vector<uint64_t> lutB, lutC;
+    if (!lt.empty()) {
+        // derived stores: the long sequences back to back, last residues keep their flags
+        auto gather = [&](const SeqSet& S, const std::vector<uint32_t>& idx, std::vector<uint64_t>& off, DevBuf& codes,
+                          DevBuf& doff, DevBuf& didx, uint64_t* maxlen) -> int {
+            off.assign(idx.size() + 1, 0);
+            *maxlen = 0;
+            for (size_t i = 0; i < idx.size(); ++i) {
+                off[i + 1] = off[i] + S.len(idx[i]);
+                *maxlen = std::max(*maxlen, S.len(idx[i]));
             }
-            continue;
-        }
+            CK(codes.ensure(kFrontPad + off.back() + kBackPad));
+            CK(doff.ensure(off.size() * 8));
+            CK(didx.ensure(std::max<size_t>(idx.size(), 1) * 4));
+            cudaStream_t st = ctx->streams[0];
+            CK(cudaMemcpyAsync(doff.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(codes.p, 0, kFrontPad, st));
+            CK(cudaMemsetAsync(codes.as<uint8_t>() + kFrontPad - 1, (int)kLastFlag, 1, st));
+            CK(cudaMemsetAsync(codes.as<uint8_t>() + kFrontPad + off.back(), 0, kBackPad, st));
+            if (!idx.empty()) {
+                CK(cudaMemcpyAsync(didx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
+                gather_seqs_kernel<<<(uint32_t)idx.size(), 128, 0, st>>>(S.dev(), didx.as<uint32_t>(), doff.as<uint64_t>(),
+                                                                        codes.as<uint8_t>() + kFrontPad);
+                CK(cudaGetLastError());
+                ctx->stats.launches++;
+            }
+            ctx->stats.h2d_bytes += off.size() * 8 + idx.size() * 4;
+            CK(cudaStreamSynchronize(st));     // idx / off are read by the copies above
+            return BSA_OK;
+        };
+        uint64_t mxT = 0, mxQ = 0;
+        rc = gather(T, lt, ltoff, ctx->lt_codes, ctx->lt_off, ctx->lt_idx, &mxT);
+        if (rc) return rc;
+        rc = gather(Q, lq, lqoff, ctx->lq_codes, ctx->lq_off, ctx->lq_idx, &mxQ);
+        if (rc) return rc;
+        lutB.resize(lt.size());
+        for (size_t i = 0; i < lt.size(); ++i) lutB[i] = first[lt[i] - t_begin];
+        lutC.resize(std::max<size_t>(lq.size(), 1), 0);
+        for (size_t i = 0; i < lq.size(); ++i) lutC[i] = lq[i];
+        CK(ctx->lutB.ensure(lutB.size() * 8));
+        CK(ctx->lutC.ensure(lutC.size() * 8));
+        CK(cudaMemcpy(ctx->lutB.p, lutB.data(), lutB.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->lutC.p, lutC.data(), lutC.size() * 8, cudaMemcpyHostToDevice));
+        ctx->stats.h2d_bytes += (lutB.size() + lutC.size()) * 8;
+        SeqStoreDev dT, dQ;
+        dT.codes = ctx->lt_codes.as<uint8_t>() + kFrontPad; dT.off = ctx->lt_off.as<uint64_t>(); dT.n = (uint32_t)lt.size();
+        dQ.codes = ctx->lq_codes.as<uint8_t>() + kFrontPad; dQ.off = ctx->lq_off.as<uint64_t>(); dQ.n = (uint32_t)lq.size();
+        var[1].xoff = &ltoff; var[1].xmax = mxT; var[1].cs_cap = bitlen(mxT);
+        var[1].qdev = dT; var[1].tdev = Q.dev(); var[1].lut = ctx->lutB.as<uint64_t>();
+        var[2].xoff = &lqoff; var[2].xmax = mxQ; var[2].cs_cap = bitlen(mxQ);
+        var[2].qdev = dQ; var[2].tdev = T.dev(); var[2].lut = ctx->lutC.as<uint64_t>();
+    }
+    // original (query, template, result index) of stream sequence x of an owner
+    auto orig_pair = [&](int v, uint32_t owner, uint32_t x, uint64_t out_base) {
+        if (v == 0) return PairReq{x, owner, out_base + x};
+        if (v == 1) return PairReq{owner, lt[x], out_base + lutB[x]};
+        return PairReq{lq[x], owner, out_base + lutC[x]};
+    };
+
+    // ---- one owner against the stream sequences [x_lo, x_hi): items of at most xb stream residues ----
+    auto plan_owner = [&](int v, uint32_t owner, uint64_t m, uint32_t x_lo, uint32_t x_hi, uint64_t out_base) -> int {
+        Variant& V = var[v];
+        const std::vector<uint64_t>& xo = *V.xoff;
+        if (x_lo >= x_hi) return BSA_OK;
         const KChoice kc = choose_k(m, C);
         if (kc.K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
         // integer-field check: score << (cs+2) must stay inside int32 for every cell
-        const int cs = std::min(bitlen(m), cs_cap);
+        const int cs = std::min(bitlen(m), V.cs_cap);
         const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
         const int64_t lim_tag = cs + kTagBits <= 27 ? (int64_t)1 << (29 - cs - kTagBits) : 0;
-        const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, Q.maxlen);
-        const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m + 4) * (int64_t)(-ctx->ge) +
+        const uint64_t m_pad = 32ull * kc.K * kc.npass;
+        const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m, V.xmax);
+        const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(V.xmax + m + 4) * (int64_t)(-ctx->ge) +
                            (int64_t)std::max(-ctx->min_m, 0);
         const bool fits = std::max(ub, lb) + 8 < lim;
         // TAG cells live in the moving frame score - (i + j) ge: [-(4 |go| + ...), max(M) min(n, m) + (n + m) |ge|]
-        const int64_t ubf = ub + (int64_t)(Q.maxlen + 32ull * kc.K * kc.npass + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+        const int64_t ubf = ub + (int64_t)(V.xmax + m_pad + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
         const int64_t lbf = 4 * (int64_t)(-ctx->go) + 8 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
         const bool fits_tag = use_tag && std::max(ubf, lbf) + 8 < lim_tag;   // room for the tag field too
-        const uint64_t m_pad = 32ull * kc.K * kc.npass;
-        uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
-        // short templates: keep items small enough that their group still fills the GPU;
+        // short owners: keep items small enough that their group still fills the GPU;
         // multi-pass: this also bounds the per-CTA boundary slice (2 MiB)
+        uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
         xb = std::min<uint64_t>(xb, 1u << 18);
-
-        // runs of non-empty queries inside [0, cnt)
+        auto emit_items = [&](uint32_t lo, uint32_t hi, bool tag) {
+            uint32_t q = lo;
+            while (q < hi) {
+                const uint64_t lim_off = xo[q] + xb;
+                uint32_t q2 = (uint32_t)(std::upper_bound(xo.begin() + q + 1, xo.begin() + hi + 1, lim_off) - xo.begin()) - 1;
+                q2 = std::max(q2, q + 1);
+                q2 = std::min(q2, hi);
+                Item it;
+                it.t = owner; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cs;
+                it.out_base = V.lut ? out_base : out_base + q;
+                Group& grp = V.groups[group_index(kc.K, kc.multi, tag)];
+                grp.items.push_back(it);
+                const uint64_t x = xo[q2] - xo[q];
+                const double sw = (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
+                padded += sw;
+                grp.swept += sw;
+                grp.cells += (double)x * (double)m;
+                if (kc.multi) grp.stride = std::max(grp.stride, x + 64);   // boundary column of one item
+                q = q2;
+            }
+        };
+        // runs of non-empty stream sequences (only the query set of variant A can hold empty ones)
         auto e_it = Q.empties.begin();
-        uint32_t run_b = qstart[t - t_begin];
-        while (run_b < cnt) {
-            while (e_it != Q.empties.end() && *e_it < run_b) ++e_it;
-            uint32_t run_e = cnt;
-            if (e_it != Q.empties.end() && *e_it < cnt) run_e = *e_it;
+        uint32_t run_b = x_lo;
+        while (run_b < x_hi) {
+            uint32_t run_e = x_hi;
+            if (v == 0) {
+                while (e_it != Q.empties.end() && *e_it < run_b) ++e_it;
+                if (e_it != Q.empties.end() && *e_it < x_hi) run_e = *e_it;
+            }
             if (run_e == run_b) {
                 // empty query: the top border value go + (m-1) ge (global.rs:81-88,143)
-                fixes.push_back(Fix{kbase + run_b, (int32_t)(ctx->go + (int64_t)(m - 1) * ctx->ge), 0u});
+                fixes.push_back(Fix{out_base + run_b, (int32_t)(ctx->go + (int64_t)(m - 1) * ctx->ge), 0u});
                 ++run_b;
                 continue;
             }
-            // items of at most xb stream residues over the queries [lo, hi)
-            auto emit_items = [&](uint32_t lo, uint32_t hi, int cshift, bool tag) {
-                uint32_t q = lo;
-                while (q < hi) {
-                    const uint64_t lim_off = Q.off[q] + xb;
-                    uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + hi + 1, lim_off) -
-                                             Q.off.begin()) - 1;
-                    q2 = std::max(q2, q + 1);
-                    q2 = std::min(q2, hi);
-                    Item it;
-                    it.t = t; it.q_begin = q; it.q_end = q2; it.cshift = (uint32_t)cshift;
-                    it.out_base = kbase + q;
-                    Group& grp = groups[group_index(kc.K, kc.multi, tag)];
-                    grp.items.push_back(it);
-                    const uint64_t x = Q.off[q2] - Q.off[q];
-                    const double sw = (double)(x + 31.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
+            if (fits_tag) emit_items(run_b, run_e, true);
+            else if (fits) emit_items(run_b, run_e, false);
+            else for (uint32_t x = run_b; x < run_e; ++x) fallback.push_back(orig_pair(v, owner, x, out_base));
+            run_b = run_e;
+        }
+        return BSA_OK;
+    };
+
+    // ---- short owners: two per warp on 16 lanes each (gotoh_pair_kernel); what cannot be paired goes to `rest` ----
+    struct POwner { uint32_t idx; uint64_t m; uint32_t lo, hi; uint64_t out_base; };
+    auto plan_pairs = [&](int v, const std::vector<POwner>& owners, std::vector<POwner>& rest) {
+        Variant& V = var[v];
+        const std::vector<uint64_t>& xo = *V.xoff;
+        std::vector<std::vector<POwner>> by_k(2 * kGroupStride);
+        const bool enabled = Q.empties.empty() && !getenv("BSA_NO_PAIR");
+        for (const POwner& o : owners) {
+            const uint64_t m = o.m;
+            bool ok = enabled && m <= 16ull * kKStream && smem_for((int)((m + 15) / 16), C) <= kSmemBudget;
+            bool tag = false;
+            if (ok) {
+                // the kernel sizes the count field for the longer owner of a pair: check with the
+                // widest field any owner of this columns-per-lane class can meet
+                const uint64_t m_class = 16ull * ((m + 15) / 16);
+                const int cs = std::min(bitlen(m_class), V.cs_cap);
+                const int64_t lim = cs <= 27 ? (int64_t)1 << (29 - cs) : 0;
+                const int64_t lim_tag = cs + kTagBits <= 27 ? (int64_t)1 << (29 - cs - kTagBits) : 0;
+                const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_class, V.xmax);
+                const int64_t lb = 4 * (int64_t)(-ctx->go) + (int64_t)(V.xmax + m_class + 4) * (int64_t)(-ctx->ge) +
+                                   (int64_t)std::max(-ctx->min_m, 0);
+                const int64_t ubf = ub + (int64_t)(V.xmax + m_class + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+                const int64_t lbf = 4 * (int64_t)(-ctx->go) + 8 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
+                ok = std::max(ub, lb) + 8 < lim;
+                tag = use_tag && std::max(ubf, lbf) + 8 < lim_tag;
+            }
+            if (ok) by_k[(m + 15) / 16 + (tag ? kGroupStride : 0)].push_back(o);
+            else rest.push_back(o);
+        }
+        for (int gk = 1; gk < 2 * kGroupStride; ++gk) {
+            const int K = gk % kGroupStride;
+            const auto& vv = by_k[gk];
+            if (K < 1 || K > kKStream) { rest.insert(rest.end(), vv.begin(), vv.end()); continue; }
+            size_t i = 0;
+            for (; i + 1 < vv.size(); i += 2) {
+                const POwner &A = vv[i], &B = vv[i + 1];
+                const uint32_t clo = std::max(A.lo, B.lo), chi = std::min(A.hi, B.hi);
+                if (clo >= chi) { rest.push_back(A); rest.push_back(B); continue; }
+                const uint64_t m_pad = 32ull * K;
+                uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
+                xb = std::min<uint64_t>(xb, 1u << 18);
+                uint32_t q = clo;
+                while (q < chi) {
+                    const uint64_t lim_off = xo[q] + xb;
+                    uint32_t q2 = (uint32_t)(std::upper_bound(xo.begin() + q + 1, xo.begin() + chi + 1, lim_off) - xo.begin()) - 1;
+                    q2 = std::min(std::max(q2, q + 1), chi);
+                    Item16 it;
+                    it.tA = A.idx; it.tB = B.idx; it.q_begin = q; it.q_end = q2;
+                    it.outA = V.lut ? A.out_base : A.out_base + q;
+                    it.outB = V.lut ? B.out_base : B.out_base + q;
+                    V.pairs[gk].items.push_back(it);
+                    const uint64_t x = xo[q2] - xo[q];
+                    const double sw = (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad;
                     padded += sw;
-                    grp.swept += sw;
-                    grp.cells += (double)x * (double)m;
-                    if (kc.multi) grp.stride = std::max(grp.stride, x + 64);   // boundary column of one item
+                    V.pairs[gk].swept += sw;
+                    V.pairs[gk].cells += (double)x * (double)(A.m + B.m);
                     q = q2;
                 }
-            };
-            auto emit_classic = [&](uint32_t lo, uint32_t hi) {
-                if (fits) emit_items(lo, hi, cs, false);
-                else for (uint32_t q = lo; q < hi; ++q) fallback.push_back(PairReq{q, t, kbase + q});
-            };
-            if (fits_tag) {
-                emit_items(run_b, run_e, cs, true);
-            } else {
-                emit_classic(run_b, run_e);
+                // what is left of either stream range goes the one-owner way
+                for (const POwner* o : {&A, &B}) {
+                    if (o->lo < clo) rest.push_back(POwner{o->idx, o->m, o->lo, clo, o->out_base});
+                    if (chi < o->hi) rest.push_back(POwner{o->idx, o->m, chi, o->hi, o->out_base});
+                }
             }
-            run_b = run_e;
+            if (i < vv.size()) rest.push_back(vv[i]);
+        }
+    };
+
+    {
+        std::vector<POwner> ownA, ownB, rest;
+        // variant A: every template that stays; empty ones are border values only
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t cnt = count_of(t);
+            if (cnt == 0 || done16[t - t_begin] || in_lt[t - t_begin]) continue;
+            const uint64_t m = T.len(t), kbase = first[t - t_begin];
+            if (m == 0) {
+                // empty template: the reference returns the row-0 border value... for an empty
+                // query against it the loop never runs: H[0]=0 (global.rs:76,143); otherwise
+                // the left border go + (n-1) ge after n rows (global.rs:99,140).
+                for (uint32_t q = 0; q < cnt; ++q) {
+                    const uint64_t n = Q.len(q);
+                    fixes.push_back(Fix{kbase + q, n == 0 ? 0 : (int32_t)(ctx->go + (int64_t)(n - 1) * ctx->ge), 0u});
+                }
+                continue;
+            }
+            ownA.push_back(POwner{t, m, 0u, cnt, kbase});
+        }
+        plan_pairs(0, ownA, rest);
+        for (const POwner& o : rest) { rc = plan_owner(0, o.idx, o.m, o.lo, o.hi, o.out_base); if (rc) return rc; }
+        if (!lt.empty()) {
+            // variant C: long template x its long queries (a prefix of the long-query store)
+            for (size_t li = 0; li < lt.size(); ++li) {
+                const uint32_t t = lt[li];
+                const uint32_t hi = (uint32_t)(std::lower_bound(lq.begin(), lq.end(), count_of(t)) - lq.begin());
+                rc = plan_owner(2, t, T.len(t), 0u, hi, first[t - t_begin]);
+                if (rc) return rc;
+            }
+            // variant B: short query x the long templates that take it (a suffix of the long-template store)
+            const uint32_t max_cnt = count_of(lt.back());
+            size_t lo = 0;
+            for (uint32_t q = 0; q < max_cnt; ++q) {
+                while (lo < lt.size() && count_of(lt[lo]) <= q) ++lo;
+                if (lo >= lt.size()) break;
+                const uint64_t n = Q.len(q);
+                if (n > Lc) continue;                    // long x long: variant C
+                ownB.push_back(POwner{q, n, (uint32_t)lo, (uint32_t)lt.size(), (uint64_t)q});
+            }
+            rest.clear();
+            plan_pairs(1, ownB, rest);
+            for (const POwner& o : rest) { rc = plan_owner(1, o.idx, o.m, o.lo, o.hi, o.out_base); if (rc) return rc; }
         }
     }
     ctx->stats.padded_cells = (uint64_t)padded;
@@ -1020,158 +1172,136 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     }
 
     // ---------------- upload the plan, launch ----------------
-    size_t n_items = 0;
-    int n_groups = 0;
-    for (auto& g : groups) { n_items += g.items.size(); n_groups += g.items.empty() ? 0 : 1; }
-    ctx->stats.items = (uint32_t)n_items;
-    CK(ctx->counters.ensure(3 * groups.size() * 4));
-    cudaStream_t s0 = ctx->streams[0];
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 3 * groups.size() * 4, s0));
-    // item lists of the paired and 16-bit plans go up before the start event, so that every
-    // stream only has to wait for that one event
-    std::vector<size_t> goff_pair(groups_pair.size(), 0), goff16(groups16.size(), 0);
-    {
-        std::vector<Item16> all;
-        for (int gk = (int)groups_pair.size() - 1; gk >= 0; --gk) {
-            goff_pair[gk] = all.size();
-            all.insert(all.end(), groups_pair[gk].items.begin(), groups_pair[gk].items.end());
-        }
-        if (!all.empty()) {
-            CK(ctx->items_pair.ensure(all.size() * sizeof(Item16)));
-            CK(cudaMemcpyAsync(ctx->items_pair.p, all.data(), all.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
-            ctx->stats.h2d_bytes += all.size() * sizeof(Item16);
-        }
-        all.clear();
-        for (int g = (int)groups16.size() - 1; g >= 0; --g) {
-            goff16[g] = all.size();
-            all.insert(all.end(), groups16[g].items.begin(), groups16[g].items.end());
-        }
-        if (!all.empty()) {
-            CK(ctx->items16.ensure(all.size() * sizeof(Item16)));
-            CK(cudaMemcpyAsync(ctx->items16.p, all.data(), all.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
-            ctx->stats.h2d_bytes += all.size() * sizeof(Item16);
-        }
-        CK(cudaStreamSynchronize(s0));   // `all` is a temporary
-    }
-    if (n_items) {
-        std::vector<Item> all;
-        all.reserve(n_items);
-        std::vector<size_t> goff(groups.size(), 0);
-        // long templates (large K) first: they are the expensive items
+    // one launch per non-empty group; long owners (large K, multi-pass) first: they are the expensive items
+    struct Launch { int v; bool pair; int g; size_t item_off; uint32_t n_items; uint64_t scr_off; };
+    std::vector<Launch> launches;
+    std::vector<Item> all;
+    std::vector<Item16> all_pair;
+    for (int v : {2, 0, 1}) {
         std::vector<int> gorder;
-        for (int g = (int)groups.size() - 1; g >= 0; --g) if (!groups[g].items.empty()) gorder.push_back(g);
+        for (int g = (int)var[v].groups.size() - 1; g >= 0; --g) if (!var[v].groups[g].items.empty()) gorder.push_back(g);
         std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) {
             return group_k(a) * (group_multi(a) ? 64 : 1) > group_k(b) * (group_multi(b) ? 64 : 1);
         });
-        for (int g : gorder) { goff[g] = all.size(); all.insert(all.end(), groups[g].items.begin(), groups[g].items.end()); }
-        CK(ctx->items.ensure(all.size() * sizeof(Item)));
-        CK(cudaMemcpyAsync(ctx->items.p, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice, s0));
-        ctx->stats.h2d_bytes += all.size() * sizeof(Item);
-        // every CTA of every concurrently running MULTI kernel owns its own boundary slice
-        uint64_t scr_total = 0;
         for (int g : gorder) {
-            if (!group_multi(g)) continue;
+            launches.push_back(Launch{v, false, g, all.size(), (uint32_t)var[v].groups[g].items.size(), 0});
+            all.insert(all.end(), var[v].groups[g].items.begin(), var[v].groups[g].items.end());
+        }
+    }
+    for (int v : {0, 1})
+        for (int gk = (int)var[v].pairs.size() - 1; gk >= 0; --gk) {
+            if (var[v].pairs[gk].items.empty()) continue;
+            launches.push_back(Launch{v, true, gk, all_pair.size(), (uint32_t)var[v].pairs[gk].items.size(), 0});
+            all_pair.insert(all_pair.end(), var[v].pairs[gk].items.begin(), var[v].pairs[gk].items.end());
+        }
+    ctx->stats.items = (uint32_t)(all.size() + all_pair.size());
+    constexpr size_t kCounters16 = 1024;     // the 16-bit groups' counters follow those of the launches above
+    CK(ctx->counters.ensure((kCounters16 + groups16.size()) * 4));
+    if (launches.size() > kCounters16) return fail(ctx, BSA_ERR_CUDA, "too many kernel groups");
+    cudaStream_t s0 = ctx->streams[0];
+    CK(cudaMemsetAsync(ctx->counters.p, 0, (kCounters16 + groups16.size()) * 4, s0));
+    // every item list goes up before the start event, so that every stream only has to wait for that one event
+    std::vector<size_t> goff16(groups16.size(), 0);
+    {
+        if (!all.empty()) {
+            CK(ctx->items.ensure(all.size() * sizeof(Item)));
+            CK(cudaMemcpyAsync(ctx->items.p, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all.size() * sizeof(Item);
+        }
+        if (!all_pair.empty()) {
+            CK(ctx->items_pair.ensure(all_pair.size() * sizeof(Item16)));
+            CK(cudaMemcpyAsync(ctx->items_pair.p, all_pair.data(), all_pair.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all_pair.size() * sizeof(Item16);
+        }
+        std::vector<Item16> all16;
+        for (int g = (int)groups16.size() - 1; g >= 0; --g) {
+            goff16[g] = all16.size();
+            all16.insert(all16.end(), groups16[g].items.begin(), groups16[g].items.end());
+        }
+        if (!all16.empty()) {
+            CK(ctx->items16.ensure(all16.size() * sizeof(Item16)));
+            CK(cudaMemcpyAsync(ctx->items16.p, all16.data(), all16.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all16.size() * sizeof(Item16);
+        }
+        CK(cudaStreamSynchronize(s0));   // `all16` is a temporary
+    }
+    // every CTA of every concurrently running MULTI kernel owns its own boundary slice
+    {
+        uint64_t scr_total = 0;
+        for (Launch& L : launches) {
+            if (L.pair || !group_multi(L.g)) continue;
             uint32_t grid = 0;
-            rc = grid_for(ctx, group_kernel(g), group_k(g), C, (uint32_t)groups[g].items.size(), &grid);
+            rc = grid_for(ctx, group_kernel(L.g), group_k(L.g), C, L.n_items, &grid);
             if (rc) return rc;
-            groups[g].scr_off = scr_total;
-            scr_total += (uint64_t)grid * groups[g].stride;
+            L.scr_off = scr_total;
+            scr_total += (uint64_t)grid * var[L.v].groups[L.g].stride;
         }
         if (scr_total) CK(ctx->scratch.ensure(scr_total * sizeof(uint2)));
-        CK(cudaEventRecord(ctx->ev_start, s0));
-        for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+    }
+    CK(cudaEventRecord(ctx->ev_start, s0));
+    for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+    {
         // BSA_PROFILE_GROUPS=1: run the groups one after another and report each one's rate
         const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
-        std::vector<cudaEvent_t> pev;
         int li = 0;
-        for (int g : gorder) {
-            const int K = group_k(g);
-            KArgs a;
-            memset(&a, 0, sizeof(a));
-            a.Q = Q.dev(); a.T = T.dev();
-            a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1;
-            a.items = ctx->items.as<Item>() + goff[g];
-            a.n_items = (uint32_t)groups[g].items.size();
-            a.item_counter = ctx->counters.as<uint32_t>() + g;
-            a.scores = d_scores; a.nident = d_nid;
-            a.scratch = ctx->scratch.as<uint2>() + groups[g].scr_off;
-            a.scratch_stride = (uint32_t)groups[g].stride;
-            if (prof_groups) {
-                cudaEvent_t e0, e1;
-                cudaEventCreate(&e0); cudaEventCreate(&e1);
-                cudaEventRecord(e0, s0);
-                rc = launch(ctx, group_kernel(g), K, a, s0);
-                cudaEventRecord(e1, s0);
-                pev.push_back(e0); pev.push_back(e1);
+        for (const Launch& L : launches) {
+            const Variant& V = var[L.v];
+            const int K = L.pair ? L.g % kGroupStride : group_k(L.g);
+            const bool tag = L.pair ? L.g >= kGroupStride : group_tag(L.g);
+            cudaStream_t st = prof_groups ? s0 : ctx->streams[li % kStreams];
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (prof_groups) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+            double cells = 0, swept = 0;
+            if (!L.pair) {
+                const Group& G = V.groups[L.g];
+                KArgs a;
+                memset(&a, 0, sizeof(a));
+                a.Q = V.qdev; a.T = V.tdev;
+                a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
+                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1;
+                a.items = ctx->items.as<Item>() + L.item_off;
+                a.n_items = L.n_items;
+                a.item_counter = ctx->counters.as<uint32_t>() + li;
+                a.scores = d_scores; a.nident = d_nid;
+                a.scratch = ctx->scratch.as<uint2>() + L.scr_off;
+                a.scratch_stride = (uint32_t)G.stride;
+                a.out_lut = V.lut; a.flip = V.flip;
+                rc = launch(ctx, group_kernel(L.g), K, a, st);
+                if (rc) return rc;
+                cells = G.cells; swept = G.swept;
             } else {
-                rc = launch(ctx, group_kernel(g), K, a, ctx->streams[li % kStreams]);
-            }
-            if (rc) return rc;
-            ++li;
-        }
-        if (prof_groups) {
-            cudaStreamSynchronize(s0);
-            size_t gi = 0;
-            for (int g : gorder) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, pev[2 * gi], pev[2 * gi + 1]);
-                fprintf(stderr, "[bsa group] K=%2d multi=%d tag=%d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n",
-                        group_k(g), group_multi(g) ? 1 : 0, group_tag(g) ? 1 : 0, groups[g].items.size(), groups[g].cells,
-                        groups[g].cells > 0 ? groups[g].swept / groups[g].cells : 0.0, ms,
-                        ms > 0 ? groups[g].cells / 1e6 / ms : 0.0);
-                cudaEventDestroy(pev[2 * gi]); cudaEventDestroy(pev[2 * gi + 1]);
-                ++gi;
-            }
-        }
-    } else {
-        CK(cudaEventRecord(ctx->ev_start, s0));
-        for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
-    }
-    // ---- paired short templates ----
-    {
-        size_t np_items = 0;
-        for (auto& g : groups_pair) np_items += g.items.size();
-        if (np_items) {
-            ctx->stats.items += (uint32_t)np_items;
-            const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
-            int li = 0;
-            for (int gk = (int)groups_pair.size() - 1; gk >= 0; --gk) {
-                if (groups_pair[gk].items.empty()) continue;
-                const int K = gk % kGroupStride;
-                const bool tag = gk >= kGroupStride;
+                const GroupPair& G = V.pairs[L.g];
                 const KernelPairFn pfn = tag ? g_pair_tag[K] : g_pair[K];
                 KArgsPair a;
                 memset(&a, 0, sizeof(a));
-                a.Q = Q.dev(); a.T = T.dev();
+                a.Q = V.qdev; a.T = V.tdev;
                 a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1; a.cs_cap = cs_cap;
-                a.items = ctx->items_pair.as<Item16>() + goff_pair[gk];
-                a.n_items = (uint32_t)groups_pair[gk].items.size();
-                a.item_counter = ctx->counters.as<uint32_t>() + 2 * groups.size() + gk;
+                a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1; a.cs_cap = V.cs_cap;
+                a.items = ctx->items_pair.as<Item16>() + L.item_off;
+                a.n_items = L.n_items;
+                a.item_counter = ctx->counters.as<uint32_t>() + li;
                 a.scores = d_scores; a.nident = d_nid;
+                a.out_lut = V.lut; a.flip = V.flip;
                 const size_t smem = smem_for(K, C);
                 uint32_t grid = 0;
                 rc = grid_for(ctx, (KernelFn)pfn, K, C, a.n_items, &grid);
                 if (rc) return rc;
-                cudaStream_t st = prof_groups ? s0 : ctx->streams[li % kStreams];
-                cudaEvent_t e0 = nullptr, e1 = nullptr;
-                if (prof_groups) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
                 pfn<<<grid, kThreads, smem, st>>>(a);
                 CK(cudaGetLastError());
                 ctx->stats.launches++;
-                if (prof_groups) {
-                    cudaEventRecord(e1, st);
-                    cudaEventSynchronize(e1);
-                    float ms = 0.f;
-                    cudaEventElapsedTime(&ms, e0, e1);
-                    fprintf(stderr, "[bsa pair ] K=%2d tag=%d items=%7zu cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n", K,
-                            tag ? 1 : 0, groups_pair[gk].items.size(), groups_pair[gk].cells,
-                            groups_pair[gk].swept / groups_pair[gk].cells, ms, ms > 0 ? groups_pair[gk].cells / 1e6 / ms : 0.0);
-                    cudaEventDestroy(e0); cudaEventDestroy(e1);
-                }
-                ++li;
+                cells = G.cells; swept = G.swept;
             }
+            if (prof_groups) {
+                cudaEventRecord(e1, st);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                fprintf(stderr, "[bsa %s %s] K=%2d multi=%d tag=%d items=%7u cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n",
+                        L.pair ? "pair " : "group", V.name, K, (!L.pair && group_multi(L.g)) ? 1 : 0, tag ? 1 : 0, L.n_items, cells,
+                        cells > 0 ? swept / cells : 0.0, ms, ms > 0 ? cells / 1e6 / ms : 0.0);
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+            }
+            ++li;
         }
     }
     // ---- 16-bit score-only groups (they follow on the same streams) ----
@@ -1206,7 +1336,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
                 a.items = ctx->items16.as<Item16>() + goff16[g];
                 a.n_items = (uint32_t)groups16[g].items.size();
-                a.item_counter = ctx->counters.as<uint32_t>() + groups.size() + g;
+                a.item_counter = ctx->counters.as<uint32_t>() + kCounters16 + g;
                 a.scores = d_scores;
                 a.scratch = ctx->scratch16.as<uint2>() + groups16[g].scr_off;
                 a.scratch_stride = (uint32_t)groups16[g].stride;

@@ -147,6 +147,13 @@ struct KArgs {
     uint32_t* dirs;         // DIRS
     uint32_t* progress;     // WAVE: boundary hand-off counters
     const uint2* wave_items;  // WAVE: (pair index, column block), in dependency order
+    // Owner swap (bsa_api.cu, "hybrid plan"): the stream set may be a derived store (the long
+    // sequences only).  out_lut[i] is then what stream sequence i contributes to the result index,
+    // k = item.out_base + out_lut[i]; flip = 1 when the ROWS are the reference's template and the
+    // columns its query: the H-max priorities of E and F trade places (global.rs:161-169 seen
+    // from the transposed matrix) and the substitution lookup is transposed.
+    const uint64_t* out_lut;
+    int flip;
 };
 
 __device__ __forceinline__ int max3_s32(int a, int b, int c) { return __vimax3_s32(a, b, c); }
@@ -321,7 +328,7 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
             int val = cs.T_PAD;
             if (c < K && col < m) {
                 const int tcode = tc[col] & kCodeMask;
-                val = ((int)subst[code * C + tcode] + cs.TSUB) * S + P3 +
+                val = ((int)subst[a.flip ? tcode * C + code : code * C + tcode] + cs.TSUB) * S + P3 +
                       ((cs.cs > 0 && tcode == code && !gap) ? 1 : 0);   // no count field when cs == 0
             }
             o[e] = val;
@@ -490,7 +497,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
                                              const uint32_t* prog_in = nullptr,
                                              uint32_t* prog_out = nullptr, LaneBest* lane_best = nullptr,
                                              const uint32_t colbase = 0, const int one2 = 1,
-                                             const int m_emit = 0) {
+                                             const int m_emit = 0, const uint64_t* __restrict__ lutp = nullptr) {
     static_assert(!TAG || (!DIRS && !LOCAL && !WAVE), "the TAG cell carries no direction bits");
     constexpr int W = KTraits<K>::W;
     constexpr int ROWB = (P16 ? ((K + 7) / 8) * 32 : KTraits<K>::ROW) * (int)sizeof(uint4);
@@ -625,7 +632,7 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
             if (!LOCAL && lastp && valid && lane == lane_last) {                                  \
                 int v = 0;                                                                        \
                 _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = HN[c];      \
-                const uint64_t k = out_idx0 + emitted;                                            \
+                const uint64_t k = out_idx0 + (lutp ? lutp[emitted] : (uint64_t)emitted);         \
                 /* TAG: out of the frame, H = H* + (n + m) ge with n = rows of this query */       \
                 if (scores) scores[k] = (v >> cs.sh) + (TAG ? (int)(pos + 1u - qstart + (uint32_t)m_emit) * cs.ge : 0); \
                 if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                       \
@@ -713,10 +720,14 @@ __device__ __forceinline__ void stream_block(const uint8_t* __restrict__ codes, 
 // Which column counts take the two-row step: measured per K on B200 (gpurun_out/qb_groups_tag*.log);
 // where the register budget forces spills (K = 11, 12 at three CTAs per SM, K = 19/20) the
 // one-row step is as fast or faster.
+#ifndef BSA_TR_FORCE
+#define BSA_TR_FORCE (-1)   // A/B only: 1 = two-row step for every K, 0 = for none, -1 = the measured table below
+#endif
+// With the 6-instruction frame cell the two-row step wins (or ties) for every K, on 32 and on 16 lanes
+// (same-box per-K A/B, profiles/r2_ab_two_rows_per_k.txt); round 1's 7-instruction cell spilled at some K.
 template <int K, bool HALF>
 struct TwoRows {
-    static constexpr bool value = BSA_TWO_ROWS && (HALF ? (K >= 8 && K != 19 && (K > BSA_MB3_MAXK || (K != 11 && K != 12)))
-                                                        : (K > BSA_MB3_MAXK && K <= 19));
+    static constexpr bool value = BSA_TR_FORCE >= 0 ? (BSA_TR_FORCE != 0) : (BSA_TWO_ROWS != 0);
 };
 
 template <int K, bool HALF>
@@ -725,7 +736,8 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
                                                   const int lane, const int lane_last, const int slot_last,
                                                   const int hdiag0, const Consts cs, const int one, const int one2,
                                                   int32_t* __restrict__ scores, uint32_t* __restrict__ nident,
-                                                  uint64_t out_idx0, const int m_emit) {
+                                                  uint64_t out_idx0, const int m_emit,
+                                                  const uint64_t* __restrict__ lutp) {
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
     constexpr int U = BSA_TAG2_U;  // double steps per loop iteration (an even count lets H[] return to its registers)
     static_assert(8 % U == 0, "the stored F get the top tag bit every 8 double steps");
@@ -774,7 +786,7 @@ __device__ __forceinline__ void stream_block_tag2(const uint8_t* __restrict__ co
         if (valid && lane == lane_last) {                                                         \
             int v = 0;                                                                            \
             _Pragma("unroll") for (int c = 0; c < K; ++c) if (c == slot_last) v = H[c];           \
-            const uint64_t k = out_idx0 + emitted;                                                \
+            const uint64_t k = out_idx0 + (lutp ? lutp[emitted] : (uint64_t)emitted);             \
             /* out of the frame: H = H* + (n + m) ge, n = rows of this query */                   \
             if (scores) scores[k] = (v >> cs.sh) + (int)((POS) + 1u - qstart + (uint32_t)m_emit) * cs.ge; \
             if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);                           \
@@ -897,7 +909,7 @@ __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__
 
 template <int K>
 __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool local = false,
-                                              bool tag = false) {
+                                              bool tag = false, bool flip = false) {
     Consts cs;
     cs.cs = cshift;
     cs.ps = cshift + (tag ? kTagBits : 0);
@@ -913,8 +925,8 @@ __device__ __forceinline__ Consts make_consts(int go, int ge, int cshift, bool l
     cs.XTOP = tag ? 1 << (cshift + kTagBits - 1) : 0;
     cs.TSUB = tag ? -2 * ge : 0;
     cs.ge = ge;
-    cs.PH = 2 << cs.ps;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
-    cs.PV = 1 << cs.ps;   // F: vertical, gap in the template
+    cs.PH = (flip ? 1 : 2) << cs.ps;   // E: horizontal, gap in the query; beats F on ties (global.rs:166-169)
+    cs.PV = (flip ? 2 : 1) << cs.ps;   // F: vertical, gap in the template   (flip: rows and columns swapped)
     cs.GOE = tag ? (go - ge) * S + cs.PH : cs.GO;
     cs.GOF = tag ? (go - ge) * S + cs.PV : cs.GO;
     // padded columns: neutral in global mode; in local mode they must never score, so that no
@@ -958,7 +970,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
         const uint64_t t0 = a.T.off[it.t];
         const uint32_t m = (uint32_t)(a.T.off[it.t + 1] - t0);
         const uint8_t* tc = a.T.codes + t0;
-        const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift, false, TAG);
+        const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift, false, TAG, a.flip != 0);
 
         // chunk schedule: big chunks over the first 13/16 of the stream, small ones over the rest,
         // so the warps reach the item's closing barrier within half a small chunk of each other
@@ -1011,12 +1023,14 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
                 if constexpr (TAG && !MULTI && TwoRows<K, false>::value)
                     stream_block_tag2<K, false>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, lane_last, slot_last,
                                                 hdiag0, cs, a.one, a.one2, a.scores, a.nident,
-                                                it.out_base + (qa - it.q_begin), (int)m);
+                                                a.out_lut ? it.out_base : it.out_base + (qa - it.q_begin), (int)m,
+                                                a.out_lut ? a.out_lut + qa : nullptr);
                 else
                     stream_block<K, false, MULTI, false, false, false, TAG>(
                         a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp, lastp ? lane_last : 31,
                         slot_last, hdiag0, cs, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores, a.nident,
-                        it.out_base + (qa - it.q_begin), nullptr, nullptr, nullptr, nullptr, nullptr, 0, a.one2, (int)m);
+                        a.out_lut ? it.out_base : it.out_base + (qa - it.q_begin), nullptr, nullptr, nullptr, nullptr,
+                        nullptr, 0, a.one2, (int)m, a.out_lut ? a.out_lut + qa : nullptr);
             }
         }
     }
@@ -1105,6 +1119,8 @@ struct KArgsPair {
     uint32_t* item_counter;
     int32_t* scores;
     uint32_t* nident;
+    const uint64_t* out_lut;   // see KArgs
+    int flip;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1450,7 +1466,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const uint32_t mmax = mA > mB ? mA : mB;
         int cshift = 32 - __clz((int)mmax);
         cshift = cshift < a.cs_cap ? cshift : a.cs_cap;
-        const Consts cs = make_consts<K>(a.go, a.ge, cshift, false, TAG);
+        const Consts cs = make_consts<K>(a.go, a.ge, cshift, false, TAG, a.flip != 0);
         const int S = 1 << cs.sh, P3 = 3 << cs.ps;
 
         const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
@@ -1489,7 +1505,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
                 int val = cs.T_PAD;
                 if (c < K && col < m) {
                     const int tcode = tc[col] & kCodeMask;
-                    val = ((int)s_subst[code * a.C + tcode] + cs.TSUB) * S + P3 + ((tcode == code && !gap) ? 1 : 0);
+                    val = ((int)s_subst[a.flip ? tcode * a.C + code : code * a.C + tcode] + cs.TSUB) * S + P3 +
+                          ((tcode == code && !gap) ? 1 : 0);
                 }
                 o[e] = val;
             }
@@ -1529,12 +1546,13 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             if constexpr (TAG && TwoRows<K, true>::value)
                 stream_block_tag2<K, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, my_last, my_slot, hdiag0, cs,
                                            a.one, a.one2, a.scores, a.nident,
-                                           (isB ? it.outB : it.outA) + (qa - it.q_begin), (int)mine);
+                                           (isB ? it.outB : it.outA) + (a.out_lut ? 0 : qa - it.q_begin), (int)mine,
+                                           a.out_lut ? a.out_lut + qa : nullptr);
             else
                 stream_block<K, false, false, false, false, true, TAG>(
                     a.Q.codes, g0, g1, prof, rsH, rsF, lane, true, true, my_last, my_slot, hdiag0, cs, a.one, nullptr,
-                    a.scores, a.nident, (isB ? it.outB : it.outA) + (qa - it.q_begin), nullptr, nullptr, nullptr,
-                    nullptr, nullptr, 0, a.one2, (int)mine);
+                    a.scores, a.nident, (isB ? it.outB : it.outA) + (a.out_lut ? 0 : qa - it.q_begin), nullptr, nullptr,
+                    nullptr, nullptr, nullptr, 0, a.one2, (int)mine, a.out_lut ? a.out_lut + qa : nullptr);
         }
     }
 }
@@ -2118,6 +2136,15 @@ __global__ void encode_kernel(const uint8_t* __restrict__ raw, uint8_t* __restri
     for (uint64_t i = nvec * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += stride)
         codes[i] = lut[raw[i]];
+}
+
+// Derived store of a subset of the sequences (the long ones, see the hybrid plan in bsa_api.cu):
+// sequence idx[i] of `src` becomes sequence i of the new store; codes keep their last-residue flags.
+__global__ void gather_seqs_kernel(const SeqStoreDev src, const uint32_t* __restrict__ idx,
+                                   const uint64_t* __restrict__ dst_off, uint8_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    const uint64_t s0 = src.off[idx[i]], len = src.off[idx[i] + 1] - s0, d0 = dst_off[i];
+    for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) dst[d0 + k] = src.codes[s0 + k];
 }
 
 __global__ void mark_last_kernel(uint8_t* __restrict__ codes, const uint64_t* __restrict__ off,
