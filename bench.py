@@ -53,8 +53,8 @@ LAW = "UniRef50-like lengths (lognormal mu=5.45 sigma=0.65, 30..4000), 25% homol
 
 # lane-instructions per cell of the dominant kernel and the bsa_measure_int_peak mix they are held against
 ROOF = {
-    # TAG cell: 4 ALU-pipe + 3 IMAD (gotoh_stream_kernel / gotoh_pair_kernel)
-    "tag": dict(ops=7.0, which=7, mix="TAG cell: VIMNMX3 + LOP3 + 2 VIADDMNMX + 3 IMAD"),
+    # frame cell (TAG kernels, round 2): 4 ALU-pipe + 2 IMAD (gotoh_stream_kernel / gotoh_pair_kernel)
+    "tag": dict(ops=6.0, which=8, mix="frame cell: VIMNMX3 + LOP3 + 2 VIADDMNMX + 2 IMAD"),
     # 16-bit packed score-only cell: 4 ALU-pipe instructions per TWO cells (gotoh_score16_kernel)
     "s16": dict(ops=2.0, which=6, mix="ALU-pipe instructions of the u16x2 cell against the VIADDMNMX.S16x2 rate"),
     # direction-store cell (gotoh_wave_kernel / gotoh_dirs_kernel): the 8-op classic cell + 4 to pack the nibble

@@ -109,9 +109,10 @@ struct bsa_ctx {
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
         raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair,
-        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC;
+        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC, wave_bnd;
     bsa_stats stats;
     uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
+    uint32_t wave_epoch = 0;    // tag of the last wavefront launch on wave_bnd
 };
 
 namespace {
@@ -334,14 +335,15 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
                 if (std::max(ub, lb) + 8 >= ((int64_t)1 << 29))
                     return fail(ctx, BSA_ERR_RANGE, "pair too long for these gap penalties / scores: score * 4 leaves int32");
             }
-            const uint64_t words = npass * (n + 32) * 32 * W;
+            const uint64_t rpl = (wave && !BSA_WAVE_P16) ? BSA_WAVE_ROWS : 1;   // rows per plane line (wave_block_rows)
+            const uint64_t words = npass * ((n + rpl - 1) / rpl + 32) * 32 * rpl * W;
             if (!recs.empty() && (dir_words + words) * 4 > dir_budget) break;
             PairRec pr;
             pr.q = r.q; pr.t = r.t; pr.out = r.out;
             pr.dir_off = dir_words;
             pr.scr_off = scr_entries;
             pr.path_off = path_bytes;
-            pr.k = (uint32_t)K;
+            pr.k = (uint32_t)K | (rpl > 1 ? (uint32_t)rpl << kPlaneRowsShift : 0u);
             pr.prog_off = wave ? (uint32_t)n_prog : 0xffffffffu;
             dir_words += words;
             if (wave) {
@@ -372,7 +374,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
                 it.cshift = 0;
                 it.out_base = 0;
                 items.push_back(it);
-                item_k.push_back((int)recs[i].k);
+                item_k.push_back((int)(recs[i].k & kPlaneKMask));
             }
             i = j;
         }
@@ -449,6 +451,18 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             a.dirs = ctx->dirs.as<uint32_t>();
             a.progress = ctx->progress.as<uint32_t>();
             a.wave_items = ctx->wave_items.as<uint2>();
+            if (BSA_WAVE_ROWS > 1 && !BSA_WAVE_P16) {
+                // the two-row blocks hand their boundary columns over as {H, epoch, E, epoch} entries in a buffer
+                // that only ever holds such entries: zeroed when (re)allocated, epochs never repeat on it
+                const size_t need = std::max<uint64_t>(scr_entries, 1) * sizeof(uint4);
+                if (need > ctx->wave_bnd.cap) {
+                    CK(ctx->wave_bnd.ensure(need));
+                    CK(cudaMemsetAsync(ctx->wave_bnd.p, 0, ctx->wave_bnd.cap, st));
+                    ctx->wave_epoch = 0;
+                }
+                a.wave_bnd = ctx->wave_bnd.as<uint4>();
+                a.epoch = ++ctx->wave_epoch;
+            }
             const size_t smem = (size_t)wave_warps * wave_smem_u4(kWaveK, C) * sizeof(uint4);
             CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
@@ -472,9 +486,14 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         ta.path_start = ctx->pstart.as<uint32_t>();
         ta.nident = d_nid;
         ta.status = ctx->status.as<uint32_t>();
-        const uint32_t tb_blocks = (ta.n_pairs + kTraceThreads / 32 - 1) / (kTraceThreads / 32);   // one warp per pair
-        if (local) traceback_local_kernel<<<tb_blocks, kTraceThreads, 0, st>>>(ta, d_lout);
-        else traceback_kernel<<<tb_blocks, kTraceThreads, 0, st>>>(ta);
+        if (local) {
+            const uint32_t tb_blocks = (ta.n_pairs + kLocalTraceThreads / 32 - 1) / (kLocalTraceThreads / 32);   // one warp per pair
+            traceback_local_kernel<<<tb_blocks, kLocalTraceThreads, 0, st>>>(ta, d_lout);
+        } else {
+            CK(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmem));
+            const uint32_t tb_blocks = (ta.n_pairs + kTraceWarps - 1) / kTraceWarps;                              // one warp per pair
+            traceback_kernel<<<tb_blocks, kTraceThreads, kTraceSmem, st>>>(ta);
+        }
         CK(cudaGetLastError());
         ctx->stats.launches++;
         uint32_t status = 0;
@@ -556,7 +575,8 @@ void bsa_destroy(bsa_ctx* c) {
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
                       &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair,
-                      &c->lt_codes, &c->lt_off, &c->lt_idx, &c->lq_codes, &c->lq_off, &c->lq_idx, &c->lutB, &c->lutC};
+                      &c->lt_codes, &c->lt_off, &c->lt_idx, &c->lq_codes, &c->lq_off, &c->lq_idx, &c->lutB, &c->lutC,
+                      &c->wave_bnd};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);

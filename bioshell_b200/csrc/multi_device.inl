@@ -163,9 +163,11 @@ int multi_align_all_pairs(bsa_ctx* c, int q_set, int t_set, const uint32_t* q_co
     if (n_results) *n_results = first[nt];
     memset(&c->stats, 0, sizeof(c->stats));
     if (first[nt] == 0) return BSA_OK;
-    // guided tiles: each takes 1/(2 workers) of what is left, never less than kMinTile cells
+    // guided tiles: each takes 1/(2 workers) of what is left, never less than kMinTile cells (a tile is a
+    // complete single-device call -- ~100 kernel groups -- so it must be worth ~0.1 s of one GPU)
     const size_t nw = c->multi->workers.size();
-    const double kMinTile = 4e10;
+    double kMinTile = 2.5e11;
+    if (const char* e = getenv("BSA_MULTI_MIN_TILE")) kMinTile = std::max(1e6, atof(e));
     std::vector<uint32_t> cut{0};
     {
         double done = 0.0;
