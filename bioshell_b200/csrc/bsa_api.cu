@@ -35,6 +35,7 @@ constexpr int kMaxSets = 8;
 constexpr int kStreams = 4;
 constexpr int kMaxCodes = 128;
 constexpr size_t kSmemBudget = 200 * 1024;   // profile bytes per CTA we are willing to use
+constexpr size_t kSmemMax = 227 * 1024;      // dynamic shared memory one CTA can opt in to (sm_100)
 constexpr int kKMax = 32;          // direction-store kernels
 constexpr int kKStream = 20;       // streaming kernels: beyond 20 columns per lane the row state no
                                    // longer fits 128 registers (2 CTAs/SM); longer templates take passes
@@ -312,22 +313,29 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         // ---- take a batch that fits the direction budget ----
         std::vector<PairRec> recs;
         std::vector<uint32_t> rec_req;
-        std::vector<uint2> wave_items;      // (rec index, column block) in dependency order
-        uint64_t dir_words = 0, scr_entries = 0, path_bytes = 0, n_prog = 0;
+        std::vector<uint32_t> wave_recs;    // K3 pairs of this batch
+        uint64_t dir_words = 0, scr_entries = 0, bnd_entries = 0, path_bytes = 0;
         // K3: templates this long run their column blocks as a wavefront over many warps
-        const int wave_warps = (int)std::min<size_t>(kWaveWarps, kSmemBudget / (wave_smem_u4(kWaveK, C) * sizeof(uint4)));
+        const size_t wave_fixed = subst_stage_bytes(C) + 2048;     // table staging + alignment slack + static
+        const int wave_warps = (int)std::min<size_t>(kWaveWarps, (kSmemMax > wave_fixed ? kSmemMax - wave_fixed : 0) / wave_region_bytes(C));
         while (pos < order.size()) {
             const PairReq& r = reqs[order[pos]];
             const uint64_t n = Q.len(r.q), m = T.len(r.t);
-            const bool wave = !local && m >= 4096 && wave_warps >= 1 &&
-                              (!BSA_WAVE_P16 || (ctx->max_m <= 8000 && ctx->min_m >= -8000));   // 16-bit profile entries hold score * 4 + 3
-              // >= 16 column blocks of 256 (kWaveK = 8)
+            bool wave = !local && m >= 4096 && wave_warps >= 1;
+            if (wave) {
+                // K3 holds (score - (i + j) ge) * 8 + 3 flag bits in an int32: the frame adds up to (n + m) |ge|
+                const uint64_t m_pad = (m + 255) / 256 * 256;
+                const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min(n, m) + (int64_t)(n + m_pad + 8) * (-(int64_t)ctx->ge);
+                const int64_t lb = 4 * (int64_t)(-(int64_t)ctx->go) + (int64_t)(n + m_pad + 8) * (-(int64_t)ctx->ge) +
+                                   (int64_t)std::max(-ctx->min_m, 0);
+                if (std::max(ub, lb) + 8 >= ((int64_t)1 << 27)) wave = false;      // the sequential passes below have 29 bits
+            }
             const int K = wave ? kWaveK : choose_dirs_k(m, C);
             if (K < 1) return fail(ctx, BSA_ERR_ALPHABET, "alphabet too large for shared memory");
             const uint64_t W = (K + 7) / 8, npass = (m + 32ull * K - 1) / (32ull * K);
-            // these kernels hold score * 4 + priority in an int32 (cs = 0): every DP value of the pair,
+            // the per-template kernels hold score * 4 + priority in an int32 (cs = 0): every DP value of the pair,
             // the borders over the padded columns and one opening below them must stay inside 29 bits
-            {
+            if (!wave) {
                 const uint64_t m_pad = npass * 32ull * K;
                 const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min(n, m);
                 const int64_t lb = 4 * (int64_t)(-(int64_t)ctx->go) + (int64_t)(n + m_pad + 4) * (-(int64_t)ctx->ge) +
@@ -335,21 +343,20 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
                 if (std::max(ub, lb) + 8 >= ((int64_t)1 << 29))
                     return fail(ctx, BSA_ERR_RANGE, "pair too long for these gap penalties / scores: score * 4 leaves int32");
             }
-            const uint64_t rpl = (wave && !BSA_WAVE_P16) ? BSA_WAVE_ROWS : 1;   // rows per plane line (wave_block_rows)
+            const uint64_t rpl = wave ? kWaveR : 1;   // rows per plane line
             const uint64_t words = npass * ((n + rpl - 1) / rpl + 32) * 32 * rpl * W;
             if (!recs.empty() && (dir_words + words) * 4 > dir_budget) break;
             PairRec pr;
             pr.q = r.q; pr.t = r.t; pr.out = r.out;
             pr.dir_off = dir_words;
-            pr.scr_off = scr_entries;
+            pr.scr_off = wave ? bnd_entries : scr_entries;
             pr.path_off = path_bytes;
             pr.k = (uint32_t)K | (rpl > 1 ? (uint32_t)rpl << kPlaneRowsShift : 0u);
-            pr.prog_off = wave ? (uint32_t)n_prog : 0xffffffffu;
+            pr.prog_off = wave ? 0u : 0xffffffffu;      // marks the K3 pairs
             dir_words += words;
             if (wave) {
-                scr_entries += (npass - 1) * n;
-                for (uint64_t ps = 0; ps < npass; ++ps) wave_items.push_back(make_uint2((uint32_t)recs.size(), (uint32_t)ps));
-                n_prog += npass;
+                bnd_entries += (npass - 1) * wave_bnd_stride(n);
+                wave_recs.push_back((uint32_t)recs.size());
             } else {
                 scr_entries += npass > 1 ? n : 0;
             }
@@ -357,6 +364,20 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             recs.push_back(pr);
             rec_req.push_back(order[pos]);
             ++pos;
+        }
+        // K3 items: (pair, column block), the pairs in order of their critical paths (rows / 4 + ~40 steps of
+        // hand-off lag per block), the blocks of a pair left to right: a block's left neighbour always comes first
+        std::vector<uint2> wave_items;
+        {
+            auto crit = [&](uint32_t ri) {
+                const uint64_t n = Q.len(recs[ri].q), m = T.len(recs[ri].t);
+                return n / 4 + 40 * ((m + 255) / 256);
+            };
+            std::stable_sort(wave_recs.begin(), wave_recs.end(), [&](uint32_t x, uint32_t y) { return crit(x) > crit(y); });
+            for (uint32_t ri : wave_recs) {
+                const uint64_t npass = (T.len(recs[ri].t) + 255) / 256;
+                for (uint64_t ps = 0; ps < npass; ++ps) wave_items.push_back(make_uint2(ri, (uint32_t)ps));
+            }
         }
         // ---- items: (template, K) runs of the batch ----
         std::vector<Item> items;
@@ -435,27 +456,23 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         }
         if (!wave_items.empty()) {
             CK(ctx->wave_items.ensure(wave_items.size() * sizeof(uint2)));
-            CK(ctx->progress.ensure(n_prog * 4));
             CK(cudaMemcpyAsync(ctx->wave_items.p, wave_items.data(), wave_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
-            CK(cudaMemsetAsync(ctx->progress.p, 0, n_prog * 4, st));
             KArgs a;
             memset(&a, 0, sizeof(a));
             a.Q = Q.dev(); a.T = T.dev();
             a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
-            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1; a.mone = -1;
             a.n_items = (uint32_t)wave_items.size();
             a.item_counter = ctx->counters.as<uint32_t>() + 63;
             a.scores = d_scores;
-            a.scratch = ctx->scratch.as<uint2>();
             a.pairs = ctx->pairs.as<PairRec>();
             a.dirs = ctx->dirs.as<uint32_t>();
-            a.progress = ctx->progress.as<uint32_t>();
             a.wave_items = ctx->wave_items.as<uint2>();
-            if (BSA_WAVE_ROWS > 1 && !BSA_WAVE_P16) {
-                // the two-row blocks hand their boundary columns over as {H, epoch, E, epoch} entries in a buffer
-                // that only ever holds such entries: zeroed when (re)allocated, epochs never repeat on it
-                const size_t need = std::max<uint64_t>(scr_entries, 1) * sizeof(uint4);
-                if (need > ctx->wave_bnd.cap) {
+            {
+                // the blocks hand their boundary columns over as {H, epoch, E, epoch} entries in a buffer that
+                // only ever holds such entries: zeroed when (re)allocated, epochs never repeat on it
+                const size_t need = std::max<uint64_t>(bnd_entries, 1) * sizeof(uint4);
+                if (need > ctx->wave_bnd.cap || ctx->wave_epoch == 0xfffffffeu) {
                     CK(ctx->wave_bnd.ensure(need));
                     CK(cudaMemsetAsync(ctx->wave_bnd.p, 0, ctx->wave_bnd.cap, st));
                     ctx->wave_epoch = 0;
@@ -463,12 +480,12 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
                 a.wave_bnd = ctx->wave_bnd.as<uint4>();
                 a.epoch = ++ctx->wave_epoch;
             }
-            const size_t smem = (size_t)wave_warps * wave_smem_u4(kWaveK, C) * sizeof(uint4);
+            const size_t smem = wave_smem_bytes(wave_warps, C) + 1024;      // + slack to align the rings to 1 KB
             CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, smem));
             if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "wavefront kernel does not fit on an SM");
-            nb = std::min(nb, kWaveCtasPerSm);
+            nb = 1;     // the wavefront is bound by its critical path: two warps per scheduler at most
             const uint32_t grid = (uint32_t)std::min<uint64_t>((wave_items.size() + wave_warps - 1) / wave_warps,
                                                                (uint64_t)nb * ctx->sms);
             gotoh_wave_kernel<<<grid, wave_warps * 32, smem, st>>>(a);
@@ -490,9 +507,14 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             const uint32_t tb_blocks = (ta.n_pairs + kLocalTraceThreads / 32 - 1) / (kLocalTraceThreads / 32);   // one warp per pair
             traceback_local_kernel<<<tb_blocks, kLocalTraceThreads, 0, st>>>(ta, d_lout);
         } else {
-            CK(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmem));
-            const uint32_t tb_blocks = (ta.n_pairs + kTraceWarps - 1) / kTraceWarps;                              // one warp per pair
-            traceback_kernel<<<tb_blocks, kTraceThreads, kTraceSmem, st>>>(ta);
+            // one warp per pair; K3 pairs walk tens of thousands of steps each: one warp per CTA and large windows
+            const bool longp = !wave_recs.empty();
+            const uint32_t tb_warps = longp ? 1u : (uint32_t)kTraceMaxWarps;
+            ta.win_bytes = longp ? kTraceWinLong : kTraceWinShort;
+            const size_t tb_smem = (size_t)tb_warps * 2 * ta.win_bytes;
+            CK(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTraceWinLong)));
+            const uint32_t tb_blocks = (ta.n_pairs + tb_warps - 1) / tb_warps;
+            traceback_kernel<<<tb_blocks, tb_warps * 32, tb_smem, st>>>(ta);
         }
         CK(cudaGetLastError());
         ctx->stats.launches++;

@@ -136,6 +136,7 @@ struct KArgs {
     int go, ge;
     int one;                // the constant 1, kept opaque to the compiler (see cell_row)
     int one2;               // a second one (TAG cell: keeps the two openings apart)
+    int mone;               // -1, as opaque as `one` (K3: a subtraction on the FMA pipe)
     const Item* items;
     uint32_t n_items;
     uint32_t* item_counter;
@@ -899,232 +900,6 @@ _Pragma("unroll")                                                               
 #undef BSA_PAIR2
 }
 
-// ---------------------------------------------------------------------------------------------
-// K3, R ROWS PER STEP, SELF-VALIDATING HAND-OFF.  One work item is ONE pair's column block (no
-// end-of-sequence flags in the stream).  The wavefront is bound by its critical path -- the rows of
-// the longest pair plus the hand-off lag of its column blocks -- so everything here is about what
-// a warp that is NOT waiting costs per row, and about waiting warps not slowing the others:
-//  * lanes skewed by R rows (R = kWaveRows = 4), the R cells of a column computed one right after
-//    the other: R independent dependency chains per warp, a quarter of the sequential steps;
-//  * the boundary column travels as 16-byte entries {H, epoch, E, epoch} (the NCCL LL pattern):
-//    the producer needs no fence and no progress counter, the consumer validates the entry it
-//    loaded (volatile, L1 bypassed) by its two epoch words and simply re-reads what is not there
-//    yet.  Round 1's ld.acquire polls invalidated the SM's L1 (CCTL.IVALL) ten times per step
-//    and the release fence cost 10 % of the producer's time (profiles/r2_ncu_summary_wave.md);
-//  * the query residues come from a 256-byte per-warp ring in shared memory, refilled 64 positions
-//    at a time one period ahead, so no global load sits in a row's dependency chain;
-//  * direction planes of these pairs are laid out per STEP of R rows, [pass][step][lane][R][W]
-//    words (PairRec::k carries R in its top bits): a warp still writes one contiguous 128 R W bytes.
-constexpr uint32_t kPlaneRowsShift = 28;                 // PairRec::k = K | rows-per-line << 28 (0 means 1)
-constexpr uint32_t kPlaneKMask = (1u << kPlaneRowsShift) - 1u;
-
-__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u4(uint4* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-
-template <int K, int R>
-__device__ __forceinline__ void wave_block_rows(const uint8_t* __restrict__ codes, const uint64_t g0, const uint32_t X,
-                                                const uint4* prof, const uint4* rsH, const uint4* rsF, const int lane,
-                                                const bool first, const bool lastp, const int lane_last,
-                                                const int slot_last, const int hdiag0, const Consts cs, const int one,
-                                                const uint4* bnd_in, uint4* bnd_out, const uint32_t epoch,
-                                                uint8_t* ring, uint32_t* __restrict__ dirs,
-                                                int32_t* __restrict__ scores, const uint64_t out_idx) {
-    static_assert(R == 2 || R == 4, "two or four rows per step");
-    constexpr int W = KTraits<K>::W;
-    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
-    constexpr uint32_t SB = 32u / R;                    // steps per boundary batch of 32 entries
-    constexpr uint32_t SR = 64u / R;                    // steps per residue refill of 64 positions
-    const bool lane0 = lane == 0;
-    const uint32_t span = lastp ? (uint32_t)lane_last : 31u;
-    const uint32_t nd = (X + R - 1u) / R + span;       // steps until the last lane of interest is through
-    const uint32_t s_emit = (uint32_t)lane_last + (X - 1u) / R;   // step in which lane_last meets the last row
-
-    int H[K], Fr[K], T[R][K];
-    load_vec<K>(H, rsH + lane);
-    load_vec<K>(Fr, rsF + lane);
-    int hdiag = hdiag0, hb = cs.hb0;
-    int oh[R], oe[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { oh[r] = 0; oe[r] = 0; }
-    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
-
-    // residue ring: slot (pos + 128) & 255 holds the code at stream position pos (relative to g0); positions
-    // before the stream (garbage rows of lanes that have not started) are clamped to the front pad, positions
-    // past the end of the query to 63 bytes behind it
-    const uint8_t* qbase = codes + g0;
-    const int pmin = -kFrontPad, pmax = (int)X + 63;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int pos = -128 + 32 * k + lane;           // [-128, 128)
-        ring[(pos + 128) & 255] = (uint8_t)ld_code(qbase + max(pmin, min(pos, pmax)));
-    }
-    __syncwarp();
-    uint32_t rf0 = 0, rf1 = 0;                          // refill in flight
-
-    // boundary column of the block to the left, 32 entries (SB steps) per batch, one entry per lane
-    uint2 ring_cur = make_uint2(0u, 0u), ring_nxt = make_uint2(0u, 0u);
-    uint4 inflight = make_uint4(0u, 0u, 0u, 0u);
-    bool mine_ok = true;                                // this lane's entry of the batch being fetched is in ring_nxt
-    uint32_t nxt_base = 0;
-    if (!first) {
-        bool ok = (uint32_t)lane >= X;
-        for (;;) {
-            if (!ok) {
-                const uint4 v = ld_volatile_u4(bnd_in + lane);
-                if (v.y == epoch && v.w == epoch) { ring_cur = make_uint2(v.x, v.z); ok = true; }
-            }
-            if (__all_sync(0xffffffffu, ok)) break;
-            __nanosleep(200);
-        }
-    }
-    // look at what came back for the next batch; ask again for what was not there yet
-#define BSA_WR_POLL()                                                                             \
-    {                                                                                             \
-        if (!mine_ok) {                                                                           \
-            if (inflight.y == epoch && inflight.w == epoch) { ring_nxt = make_uint2(inflight.x, inflight.z); mine_ok = true; } \
-            else inflight = ld_volatile_u4(bnd_in + nxt_base + lane);                             \
-        }                                                                                         \
-    }
-
-    for (uint32_t S = 0; S < nd; ++S) {
-        const uint32_t r0 = R * S;                      // lane 0's rows of this step: r0 .. r0 + R - 1
-        // ---- residue ring: positions [R S + 64, R S + 128) are requested at S % SR == 0, stored SR / 2 steps later ----
-        if ((S & (SR - 1u)) == 0u) {
-            const int pos = (int)r0 + 64 + 2 * lane;
-            rf0 = ld_code(qbase + min(pos, pmax));
-            rf1 = ld_code(qbase + min(pos + 1, pmax));
-        } else if ((S & (SR - 1u)) == SR / 2u) {
-            const int pos = (int)(r0 - 32u) + 64 + 2 * lane;
-            ring[(pos + 128) & 255] = (uint8_t)rf0;
-            ring[(pos + 129) & 255] = (uint8_t)rf1;
-            __syncwarp();
-        }
-        const int mypos = (int)r0 - R * lane;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t b = ring[(mypos + r + 128) & 255];
-            load_vec<K>(T[r], reinterpret_cast<const uint4*>(prof_lane + (b & kCodeMask) * ROWB));
-        }
-        // ---- boundary batches: the next one is asked for at S % SB == 1 and looked at every other step ----
-        if (!first) {
-            if ((S & (SB - 1u)) == 1u) {
-                nxt_base = (r0 & ~31u) + 32u;
-                mine_ok = nxt_base + (uint32_t)lane >= X;
-                if (!mine_ok) inflight = ld_volatile_u4(bnd_in + nxt_base + lane);
-            } else if ((S & 1u) == 1u) {
-                BSA_WR_POLL()
-            }
-        }
-        int hin[R], er[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            hin[r] = __shfl_up_sync(0xffffffffu, oh[r], 1);
-            er[r] = __shfl_up_sync(0xffffffffu, oe[r], 1);
-        }
-        if (!first) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t bx = __shfl_sync(0xffffffffu, ring_cur.x, (r0 + r) & 31u);
-                const uint32_t by = __shfl_sync(0xffffffffu, ring_cur.y, (r0 + r) & 31u);
-                if (lane0) { hin[r] = (int)bx; er[r] = (int)by; }
-            }
-            if ((S & (SB - 1u)) == SB - 1u) {
-                // the last entries of the batch were just taken: the next batch must be complete now
-                for (;;) {
-                    BSA_WR_POLL()
-                    if (__all_sync(0xffffffffu, mine_ok)) break;
-                    __nanosleep(100);
-                }
-                ring_cur = ring_nxt;
-            }
-        } else if (lane0) {
-            // H[i][0] = go + (i-1) ge; E[i][1] opens from it (global.rs:96-101)
-#pragma unroll
-            for (int r = 0; r < R; ++r) { hin[r] = hb + r * cs.GEB; er[r] = hin[r] + cs.GO; }
-        }
-        hb += R * cs.GEB;
-        int hd[R];
-        hd[0] = hdiag;
-#pragma unroll
-        for (int r = 1; r < R; ++r) hd[r] = hin[r - 1];
-        hdiag = hin[R - 1];
-        uint32_t dw[R][W];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-            for (int w = 0; w < W; ++w) dw[r][w] = 0u;
-        }
-        int cap[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) cap[r] = 0;
-        // the R x K cells of this step; CAP: the one step in which H[n][m] appears (a second copy of the
-        // body, so that the capture costs the other steps nothing)
-#define BSA_WR_CELLS(CAP)                                                                         \
-        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                           \
-            int fraw = Fr[c];            /* F handed down the rows of this column */                \
-            int habove = H[c];           /* H of the row above, same column: the next column's diagonal */ \
-            _Pragma("unroll") for (int r = 0; r < R; ++r) {                                       \
-                const int e = er[r] | cs.PH;                                                      \
-                const int f = fraw | cs.PV;                                                       \
-                const int d = hd[r] * one + T[r][c];                                              \
-                const int h = max3_s32(d, e, f);                                                  \
-                dw[r][c >> 3] = (dw[r][c >> 3] << 4) | ((uint32_t)h & 3u) | ((((uint32_t)er[r] | (uint32_t)fraw) & 3u) << 2); \
-                const int hc = h & cs.MASK;                                                       \
-                const int hg = hc * one + cs.GO;                                                  \
-                er[r] = addmax_s32(e, cs.GE, hg);                                                 \
-                fraw = addmax_s32(f, cs.GE, hg);                                                  \
-                hd[r] = habove;                                                                   \
-                habove = hc;                                                                      \
-                if (c == K - 1) oh[r] = hc;                                                       \
-                if (CAP && c == slot_last) cap[r] = hc;                                           \
-            }                                                                                     \
-            H[c] = habove;                                                                        \
-            Fr[c] = fraw;                                                                         \
-        }
-        if (S != s_emit) {
-            BSA_WR_CELLS(false)
-        } else {
-            BSA_WR_CELLS(true)
-            if (lastp && lane == lane_last && scores) {
-                int v = cap[0];
-#pragma unroll
-                for (int r = 1; r < R; ++r) if (((X - 1u) % R) == (uint32_t)r) v = cap[r];
-                scores[out_idx] = v >> cs.sh;
-            }
-        }
-#undef BSA_WR_CELLS
-#pragma unroll
-        for (int r = 0; r < R; ++r) oe[r] = er[r];
-        {
-            uint32_t* dp = dirs + ((size_t)S * 32 + lane) * (R * W);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-#pragma unroll
-                for (int w = 0; w < W; ++w) dp[r * W + w] = dw[r][w];
-            }
-        }
-        if (!lastp && lane == 31) {
-            const uint32_t q0 = r0 - 31u * R;           // lane 31's rows; wraps below row 0 -> fails the bound tests
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (q0 + r < X) st_volatile_u4(bnd_out + q0 + r, (uint32_t)oh[r], epoch, (uint32_t)oe[r], epoch);
-        }
-        // a lane's rows before the stream starts are garbage: put it on the top border right before its first real row
-        if (S < 31u && S + 1u == (uint32_t)lane) {
-            load_vec<K>(H, rsH + lane);
-            load_vec<K>(Fr, rsF + lane);
-            hdiag = hdiag0;
-        }
-    }
-#undef BSA_WR_POLL
-}
 
 __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
                                                     uint32_t hi, uint64_t x) {
@@ -1925,158 +1700,11 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
     }
 }
 
-// K3 -- intra-task wavefront for long pairs.  Every WARP is an independent worker with its own
-// profile slice in shared memory; work items are (pair, column block) claimed in dependency
-// order from a global counter, so the block to the left of a claimed item is always already
-// running (or done) and the spin-wait on its progress counter cannot deadlock.  The column
-// blocks of one pair thus sweep the DP matrix as a staggered wavefront over many SMs.
-#ifndef BSA_WAVE_K
-#define BSA_WAVE_K 8
-#endif
-#ifndef BSA_WAVE_ROWS
-#define BSA_WAVE_ROWS 4       // K3: rows per step (wave_block_rows) = rows per line of the direction planes; 2 and 1 (round 1's block): A/B only
-#endif
-#ifndef BSA_WAVE_WARPS
-#define BSA_WAVE_WARPS 8
-#endif
-#ifndef BSA_WAVE_CTAS_PER_SM
-#define BSA_WAVE_CTAS_PER_SM 1
-#endif
-// shared memory of one wavefront worker (uint4 units): C profile rows + the two border rows
-__host__ __device__ constexpr int wave_prof_row(int K) { return BSA_WAVE_P16 ? ((K + 7) / 8) * 32 : ((K + 3) / 4) * 32; }
-__host__ __device__ constexpr size_t wave_smem_u4(int K, int C) {
-    return BSA_WAVE_P16 ? (size_t)C * wave_prof_row(K) + 2u * (size_t)(((K + 3) / 4) * 32)
-                        : (size_t)(C + 2) * (((K + 3) / 4) * 32);
-}
-constexpr int kWaveK = BSA_WAVE_K;        // 32 K columns per block (256)
-constexpr int kWaveWarps = BSA_WAVE_WARPS;
-constexpr int kWaveCtasPerSm = BSA_WAVE_CTAS_PER_SM;   // the wavefront is bound by its critical path: fewer warps per scheduler = faster rows
+}  // namespace bsa
+#include "wave_kernels.cuh"
+namespace bsa {
 
-__global__ void __launch_bounds__(kWaveWarps * 32) gotoh_wave_kernel(const KArgs a) {
-    extern __shared__ uint4 smem[];
-    __shared__ uint8_t s_ring[kWaveWarps][256];      // wave_block2: per-warp ring of query residues
-    constexpr int K = kWaveK;
-    constexpr int ROW = KTraits<K>::ROW;
-    constexpr int W = KTraits<K>::W;
-    constexpr bool P16 = BSA_WAVE_P16 != 0;
-    constexpr int PROW = wave_prof_row(K);      // uint4 per profile row (16-bit entries: 8 per uint4)
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int C = a.C;
-    uint4* prof = P16 ? smem + (size_t)warp * wave_smem_u4(K, C) : smem + (size_t)warp * (C + 2) * ROW;
-    uint4* rsH = P16 ? prof + (size_t)C * PROW : prof + (size_t)C * ROW;
-    uint4* rsF = rsH + ROW;
-    const Consts cs = make_consts<K>(a.go, a.ge, 0);
-    const int S = 4, P3 = 3;
-
-    for (;;) {
-        uint32_t wi = 0;
-        if (lane == 0) wi = atomicAdd(a.item_counter, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= a.n_items) break;
-        const uint2 item = a.wave_items[wi];
-        const PairRec pr = a.pairs[item.x];
-        const uint32_t pass = item.y;
-        const uint64_t t0 = a.T.off[pr.t];
-        const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - t0);
-        const uint8_t* tc = a.T.codes + t0;
-        const uint32_t npass = (m + 32 * K - 1) / (32 * K);
-        const uint32_t colbase = pass * 32 * K;
-        const uint64_t g0 = a.Q.off[pr.q], g1 = a.Q.off[pr.q + 1];
-        const uint32_t n = (uint32_t)(g1 - g0);
-
-        // warp-private profile of this column block (same layout as build_profile)
-        __syncwarp();
-        if (P16) {
-            for (int idx = lane; idx < C * PROW; idx += 32) {
-                const int code = idx / PROW, r = idx - code * PROW, v = r >> 5, ln = r & 31;
-                uint32_t o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    uint32_t h2[2];
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int c = 8 * v + 2 * e + hh;
-                        const uint32_t col = colbase + ln * K + c;
-                        const int val = (c < K && col < m) ? (int)a.subst[code * C + (tc[col] & kCodeMask)] * S + P3 : cs.T_PAD;
-                        h2[hh] = (uint32_t)val & 0xffffu;      // |score * 4 + 3| < 2^15 (host range check on the matrix)
-                    }
-                    o[e] = h2[0] | (h2[1] << 16);
-                }
-                prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-        } else
-        for (int idx = lane; idx < C * ROW; idx += 32) {
-            const int code = idx / ROW, r = idx - code * ROW, v = r >> 5, ln = r & 31;
-            int o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = 4 * v + e;
-                const uint32_t col = colbase + ln * K + c;
-                o[e] = (c < K && col < m) ? (int)a.subst[code * C + (tc[col] & kCodeMask)] * S + P3 : cs.T_PAD;
-            }
-            prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        for (int r = lane; r < ROW; r += 32) {
-            const int v = r >> 5, ln = r & 31;
-            int h[4], f[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const long long j = (long long)colbase + ln * K + 4 * v + e + 1;
-                h[e] = (int)((a.go + (j - 1) * a.ge) * S);
-                f[e] = h[e] + cs.GO;
-            }
-            rsH[r] = make_uint4(h[0], h[1], h[2], h[3]);
-            rsF[r] = make_uint4(f[0], f[1], f[2], f[3]);
-        }
-        __syncwarp();
-
-        const bool lastp = (pass + 1 == npass);
-        const int lane_last = (int)((m - 1 - colbase) / K);
-        const int slot_last = (int)((m - 1 - colbase) % K);
-        const long long jl = (long long)colbase + (long long)lane * K;
-        const int hdiag0 = jl == 0 ? 0 : (int)((a.go + (jl - 1) * a.ge) * S);
-        uint2* bnd = a.scratch + pr.scr_off;          // (npass - 1) boundary columns of n entries
-        uint32_t* prog = a.progress + pr.prog_off;
-        if constexpr (!P16 && BSA_WAVE_ROWS > 1) {
-            // planes per step of R rows: ((n + R - 1) / R + 32) steps x 32 lanes x R W words
-            constexpr uint32_t R = BSA_WAVE_ROWS;
-            uint32_t* dirs2 = a.dirs + pr.dir_off + (size_t)pass * (size_t)((n + R - 1u) / R + 32u) * 32 * (R * W);
-            // boundary columns: (npass - 1) x n self-validating 16-byte entries in the wavefront's own buffer
-            uint4* bnd4 = a.wave_bnd + pr.scr_off;
-            wave_block_rows<K, BSA_WAVE_ROWS>(a.Q.codes, g0, n, prof, rsH, rsF, lane, pass == 0, lastp, lastp ? lane_last : 31,
-                                              slot_last, hdiag0, cs, a.one, pass ? bnd4 + (size_t)(pass - 1) * n : nullptr,
-                                              lastp ? nullptr : bnd4 + (size_t)pass * n, a.epoch, s_ring[warp], dirs2,
-                                              a.scores, pr.out);
-            continue;
-        }
-        uint32_t* dirs = a.dirs + pr.dir_off + (size_t)pass * (size_t)(n + 32) * 32 * W;
-        stream_block<K, true, true, true, false, false, false, P16>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, pass == 0, lastp,
-                                          lastp ? lane_last : 31, slot_last, hdiag0, cs, a.one,
-                                          pass ? bnd + (size_t)(pass - 1) * n : nullptr, a.scores, nullptr,
-                                          pr.out, dirs, lastp ? nullptr : bnd + (size_t)pass * n,
-                                          pass ? prog + (pass - 1) : nullptr, lastp ? nullptr : prog + pass);
-    }
-}
-
-// Walks the stored directions exactly as GlobalAligner::backtrace does
-// (global.rs:146-201): state H follows diag > E > F, state E/F keeps going while the
-// cell it leaves was an extension.  One thread per pair; writes the path glyphs
-// backwards into the pair's slot and counts identical residues on the way
-// (raw-byte equality == code equality; '-'/'_' never count, msa.rs:264).
-struct TraceArgs {
-    SeqStoreDev Q, T;
-    const PairRec* pairs;
-    uint32_t n_pairs;
-    const uint32_t* dirs;
-    const uint8_t* isgap;
-    uint32_t ncodes;        // entries of isgap
-    uint8_t* path;          // may be null (identity only)
-    uint32_t* path_start;   // per pair (by position in `pairs`): first byte of the path in its slot
-    uint32_t* nident;       // indexed by PairRec::out, may be null
-    uint32_t* status;       // set to 1 if an invalid direction is met
-};
-
+// Local-alignment walk (traceback_local_kernel).
 // One WARP walks one pair; all 32 lanes run the same (uniform) walk, lane 0 writes.  The walk mostly
 // moves diagonally, i.e. one step (a new 128-byte line) back per glyph, and every load depends on
 // the previous one: the warp therefore keeps the direction words of the current (pass, lane, word)
@@ -2129,142 +1757,6 @@ struct ColCursor {
     }
 };
 
-// GlobalAligner::backtrace on the device, one WARP per pair (all lanes run the same uniform walk,
-// lane 0 writes).  The walk reads one direction nibble per step and every read depends on the one
-// before, so its cost is the latency of a lookup.  The direction words are therefore STAGED: the
-// planes are step-major, i.e. the lines (all 32 lanes' words of one step) of consecutive steps are
-// contiguous, and the walk moves up about one line per step.  Each warp keeps two windows of
-// kTraceWinBytes in shared memory, filled by the bulk-copy engine (cp.async.bulk + mbarrier, UBLKCP):
-// the window the walk is in, and the one above it, requested as soon as the walk enters the
-// current one -- a lookup is then a shared-memory load, and HBM latency is paid once per column
-// block change instead of once per window.
-constexpr int kTraceWarps = 4;                 // pairs per CTA
-constexpr uint32_t kTraceWinBytes = 8192;      // 64 lines of a one-word plane (K <= 8), 32 double steps of a two-row one
-constexpr int kTraceThreads = kTraceWarps * 32;
-constexpr size_t kTraceSmem = (size_t)kTraceWarps * 2 * kTraceWinBytes;
-
-__global__ void __launch_bounds__(kTraceThreads) traceback_kernel(const TraceArgs a) {
-    extern __shared__ uint4 tb_smem[];
-    __shared__ uint64_t tb_bar[kTraceWarps][2];
-    const uint32_t warp = threadIdx.x >> 5, me = threadIdx.x & 31u;
-    const uint32_t p = blockIdx.x * kTraceWarps + warp;
-    const bool writer = me == 0;
-    if (p >= a.n_pairs) return;                // whole warps leave; the barriers below are per warp
-    const PairRec pr = a.pairs[p];
-    const uint8_t* qc = a.Q.codes + a.Q.off[pr.q];
-    const uint8_t* tc = a.T.codes + a.T.off[pr.t];
-    const uint32_t n = (uint32_t)(a.Q.off[pr.q + 1] - a.Q.off[pr.q]);
-    const uint32_t m = (uint32_t)(a.T.off[pr.t + 1] - a.T.off[pr.t]);
-    const uint32_t rpl = (pr.k >> kPlaneRowsShift) ? (pr.k >> kPlaneRowsShift) : 1u;   // rows per line (K3: wave_block_rows), 1, 2 or 4
-    const uint32_t rsh = rpl == 4u ? 2u : (rpl == 2u ? 1u : 0u);
-    const uint32_t K = pr.k & kPlaneKMask, W = (K + 7) / 8;
-    const uint32_t LW = 32u * W * rpl;                  // words per line (all lanes' words of one step)
-    const uint32_t nlines = ((n + rpl - 1u) >> rsh) + 32u;
-    const size_t plane = (size_t)nlines * LW;
-    const uint32_t R = kTraceWinBytes / (LW * 4u);      // lines per window (>= 8 for K <= 32)
-    const uint32_t* dirs = a.dirs + pr.dir_off;
-    uint8_t* out = (a.path && writer) ? a.path + pr.path_off : nullptr;
-    // buffers and barriers are addressed arithmetically (no dynamically indexed local arrays)
-    uint32_t* const win0 = reinterpret_cast<uint32_t*>(tb_smem) + (size_t)(warp * 2) * (kTraceWinBytes / 4);
-    uint64_t* const bar0 = &tb_bar[warp][0];
-    if (writer) { TmaStage::init(bar0); TmaStage::init(bar0 + 1); }
-    __syncwarp();
-    uint32_t phases = 0u;                   // bit b: parity the next completion of buffer b will have
-    // window state: buffer `cb` holds lines [lo, hi) of column block `wpass`; the other buffer has lines [nlo, lo) in flight
-    uint32_t cb = 0, wpass = 0xffffffffu, lo = 0, hi = 0, nlo = 0;
-    bool have_next = false;
-    auto request = [&](uint32_t buf, uint32_t pass, uint32_t l0, uint32_t l1) {   // lines [l0, l1) of `pass` into `buf`
-        __syncwarp();                       // every lane is done reading what the buffer held
-        if (writer) {
-            const uint32_t bytes = (l1 - l0) * LW * 4u;
-            TmaStage::arm(bar0 + buf, bytes);
-            TmaStage::copy(bar0 + buf, win0 + buf * (kTraceWinBytes / 4), dirs + pass * plane + (size_t)l0 * LW, bytes);
-        }
-    };
-    auto ready = [&](uint32_t buf) {
-        TmaStage::wait(bar0 + buf, (phases >> buf) & 1u);
-        phases ^= 1u << buf;
-    };
-
-    uint32_t pos = n + m, i = n, j = m, nid = 0;
-    int st = 0;
-    // '-' / '_' codes as bit masks (msa.rs:264), so the identity test is register-only
-    unsigned long long gap_lo = 0ull, gap_hi = 0ull;
-    for (uint32_t code = 0; code < a.ncodes; ++code)
-        if (a.isgap[code]) {
-            if (code < 64) gap_lo |= 1ull << code; else gap_hi |= 1ull << (code - 64);
-        }
-    ColCursor cur;
-    if (j > 0) cur.init(K, j);
-    // the residues of a diagonal step are only needed for the count: they are consumed one
-    // diagonal step later, so their loads never stall the walk
-    uint32_t px = 0xffu, py = 0xfeu;
-    bool bad = false;
-#define BSA_COUNT_PENDING() \
-    nid += (px == py && !((((px & 64u) ? gap_hi : gap_lo) >> (px & 63u)) & 1ull)) ? 1u : 0u;
-    while (i > 0 && j > 0) {
-        const uint32_t line = ((i - 1u) >> rsh) + cur.lane;
-        if (cur.pass != wpass || line < lo || line >= hi) {                 // warp-uniform
-            if (cur.pass == wpass && have_next && line >= nlo && line < lo) {
-                // the walk moved up into the window that was requested ahead
-                cb ^= 1u;
-                ready(cb);
-                hi = lo;
-                lo = nlo;
-            } else {
-                if (have_next) { ready(cb ^ 1u); }                           // drain the request in flight
-                wpass = cur.pass;
-                hi = line + 1u;
-                lo = hi > R ? hi - R : 0u;
-                request(cb, wpass, lo, hi);
-                ready(cb);
-            }
-            have_next = lo > 0u;
-            if (have_next) {
-                nlo = lo > R ? lo - R : 0u;
-                request(cb ^ 1u, wpass, nlo, lo);
-            }
-        }
-        const uint32_t wofs = (line - lo) * LW + (cur.lane * rpl + ((i - 1u) & (rpl - 1u))) * W + cur.word();
-        const uint32_t nib = (win0[cb * (kTraceWinBytes / 4) + wofs] >> cur.shift()) & 15u;
-        if (st == 0) {
-            const uint32_t hd = nib & 3u;
-            if (hd == 3u) {
-                --pos;
-                if (out) out[pos] = '*';
-                BSA_COUNT_PENDING()
-                px = qc[i - 1] & kCodeMask;
-                py = tc[j - 1] & kCodeMask;
-                --i; --j;
-                cur.left();
-            } else if (hd == 2u) st = 1;
-            else if (hd == 1u) st = 2;
-            else { bad = true; break; }
-        } else if (st == 1) {
-            --pos;
-            if (out) out[pos] = '-';
-            --j;
-            cur.left();
-            st = (nib & 8u) ? 1 : 0;
-        } else {
-            --pos;
-            if (out) out[pos] = '|';
-            --i;
-            st = (nib & 4u) ? 2 : 0;
-        }
-    }
-    BSA_COUNT_PENDING()
-#undef BSA_COUNT_PENDING
-    if (have_next) ready(cb ^ 1u);          // nothing of this warp stays in flight when it leaves
-    if (bad && writer) *a.status = 1u;
-    // borders: row 0 is all E-extensions, column 0 all F-extensions (global.rs:81-88,96-97)
-    while (j > 0) { --pos; if (out) out[pos] = '-'; --j; }
-    while (i > 0) { --pos; if (out) out[pos] = '|'; --i; }
-    if (writer) {
-        a.path_start[p] = pos;
-        if (a.nident) a.nident[pr.out] = nid;
-    }
-}
 
 // Local alignment (LocalAlignment::align, bioshell-seq/src/alignment/local.rs:83-207): the
 // direction-store kernel with LOCAL recurrences.  Every lane tracks the first strict maximum of

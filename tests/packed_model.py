@@ -179,6 +179,102 @@ def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
     return (v >> (cs + xb + 2)) + (n + m) * ge, v & (U - 1)
 
 
+def wave_frame_align(q, t, score, aa, go, ge, pre=4):
+    """Scalar model of the K3 wavefront cell (wave_kernels.cuh, wave_block_frame + traceback_kernel):
+    v = (score - (i + j) ge) << 3 | prio << 1 | m.  The rows are padded at the TOP to a multiple of 4 with
+    rows of a pad residue (profile entry 6 = score 0, priority 3) -- `pre` more such rows model the steps a
+    lane spends before its first row -- columns are padded on the right to a multiple of 256.  Returns
+    (score, path, words) where words[(t, lane_block)] is the 32-bit direction word of padded row t."""
+    n, m = len(q), len(t)
+    pad = (4 - n % 4) % 4
+    mp = (m + 255) // 256 * 256
+    HB = (go - ge) * 8
+    GOE, GOF = HB + 4, HB + 2
+    EB, FB = HB + GOE, HB + GOF
+
+    def T(a, c):
+        if a is None or c >= m:
+            return 6
+        return (score[aa[a] * 21 + aa[t[c]]] - 2 * ge) * 8 + 6
+
+    H = [HB] * mp
+    F = [FB] * mp
+    words = {}
+    hin_prev = HB                      # H of the left border one row up (the diagonal of column 1)
+    for tt in range(-pre, n + pad):
+        a = q[tt - pad] if tt >= pad else None
+        # left border entry of this row (block 0's ring): H*[i][0], E*[i][1]; H*[0][0] = 0 sits on the row
+        # right above row 1 (the last padding row, or -- no padding -- the initial diagonal)
+        hin, er = HB, EB
+        if tt == pad - 1:
+            hin = 0
+        hd = hin_prev
+        if tt == 0 and pad == 0 and pre == 0:
+            hd = 0
+        if pad == 0 and tt == 0 and pre > 0:
+            hd = 0                     # the kernel: hdiag of (block 0, lane 0) starts at 0 when there is no padding
+        dA = dF = 0
+        for c in range(mp):
+            f = F[c]
+            d = hd + T(a, c)
+            h = max(d, er, f)
+            dA = ((dA >> 3) | ((((h & ~1) | (er & 1)) & 7) << 29)) & 0xffffffff
+            f1 = f | 1
+            dF = (dF * 2 + f1 - f) & 0xffffffff
+            hc = h & ~7
+            er = max(hc + GOE, er | 1)
+            F[c] = max(hc + GOF, f1)
+            hd, H[c] = H[c], hc
+            if c % 8 == 7:
+                if tt >= 0:
+                    words[(tt, c // 8)] = (dA & 0xffffff00) | (dF & 0xff)
+                dA = dF = 0
+        hin_prev = hin
+        for v in H + F:
+            assert -(1 << 31) <= v < (1 << 31)
+    if m == 0:
+        return (0 if n == 0 else go + (n - 1) * ge), "|" * n, words
+    if n == 0:
+        return go + (m - 1) * ge, "-" * m, words
+    sc = (H[m - 1] >> 3) + (n + m) * ge
+
+    def look(i, j):
+        w = words[(i - 1 + pad, (j - 1) // 8)]
+        c = (j - 1) % 8
+        a3 = (w >> (8 + 3 * c)) & 7
+        return a3 >> 1, a3 & 1, ((w >> (7 - c)) & 1) ^ 1
+
+    # the run-based walk of traceback_kernel: 32 cells ahead in the current direction at a time
+    out, i, j, st = [], n, m, 0
+    while i > 0 and j > 0:
+        cells = []
+        for k in range(32):
+            ii, jj = (i - k if st != 1 else i), (j - k if st != 2 else j)
+            ok = ii >= 1 and jj >= 1 and (jj - 1) // 256 == (j - 1) // 256
+            cells.append(look(ii, jj) if ok else None)
+        flags = [c is not None and (c[0] == 3 if st == 0 else c[st] == 1) for c in cells]
+        t1 = flags.index(False) if False in flags else 32
+        seen = t1 < 32 and cells[t1] is not None
+        if st == 0:
+            out += ["*"] * t1
+            i -= t1; j -= t1
+            if seen:
+                hd = cells[t1][0]
+                assert hd in (1, 2)
+                st = 1 if hd == 2 else 2
+        else:
+            run = t1 + (1 if seen else 0)
+            out += ["-" if st == 1 else "|"] * run
+            if st == 1:
+                j -= run
+            else:
+                i -= run
+            if seen:
+                st = 0
+    out += ["-"] * j + ["|"] * i
+    return sc, "".join(reversed(out)), words
+
+
 def wave_ring_schedule(X, WB=32, PF=8, U=2, span=31):
     """Scalar model of the boundary hand-off of the K3 wavefront consumer (stream_block with WRING,
     gotoh_kernels.cuh): which boundary entry lane 0 takes at every step and how many entries must

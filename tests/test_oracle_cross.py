@@ -121,6 +121,27 @@ def test_frame_lane_model_matches_oracle(alphabet):
             assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R)
 
 
+@pytest.mark.parametrize("alphabet", [AA, DIRTY])
+def test_wave_frame_cell_model_matches_oracle(alphabet):
+    """The K3 direction-frame cell ((score - (i+j) ge) << 3 | prio << 1 | m, rows padded at the top with a
+    zero-score residue, 3 + 1 direction bits per cell) and the run-based walk over its words give the
+    reference's score and path glyph for glyph -- every query length mod 4, with and without the rows a
+    lane spends ahead of its first row."""
+    from packed_model import wave_frame_align
+    text = ncbi_text("BLOSUM62")
+    sc, ai = c_oracle.parse_ncbi(text)
+    psc, pai = pyoracle.parse_ncbi(text)
+    k = 0
+    for q, t in pairs(77, 60, 90, alphabet):
+        go, ge = GAPS[k % len(GAPS)]
+        k += 1
+        ref = c_oracle.align_pair(q, t, sc, ai, go, ge, max(len(q), len(t)) + 100 * (k % 3))
+        for pre in (0, 4):
+            s, path, _ = wave_frame_align(q, t, psc, pai, go, ge, pre=pre)
+            assert s == ref["score"], (q, t, go, ge, pre)
+            assert path == ref["path"], (q, t, go, ge, pre)
+
+
 def test_orientation_matters_for_identity_not_score():
     """SURVEY.md 8a note 5: swapping query and template keeps the score but can change the
     path/identity, so the kernels must keep the reference's orientation."""
