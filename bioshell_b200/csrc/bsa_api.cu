@@ -486,11 +486,32 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, smem));
             if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "wavefront kernel does not fit on an SM");
             nb = 1;     // the wavefront is bound by its critical path: two warps per scheduler at most
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((wave_items.size() + wave_warps - 1) / wave_warps,
-                                                               (uint64_t)nb * ctx->sms);
+            // one CTA per SM, as many as there are items: the kernel deals the items out round-robin over the CTAs
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(wave_items.size(), (uint64_t)nb * ctx->sms);
+            const char* trace_path = getenv("BSA_WAVE_TRACE");     // diagnostics: per-item start / end times
+            unsigned long long* d_trace = nullptr;
+            if (trace_path) {
+                CK(cudaMalloc(&d_trace, wave_items.size() * 32));
+                CK(cudaMemsetAsync(d_trace, 0, wave_items.size() * 32, st));
+                a.wave_trace = d_trace;
+            }
             gotoh_wave_kernel<<<grid, wave_warps * 32, smem, st>>>(a);
             CK(cudaGetLastError());
             ctx->stats.launches++;
+            if (trace_path) {
+                std::vector<unsigned long long> tr(wave_items.size() * 4);
+                CK(cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                cudaFree(d_trace);
+                if (FILE* f = fopen(trace_path, "w")) {
+                    fprintf(f, "item,pair,block,n,m,start_ns,end_ns,sm,warp,steps\n");
+                    for (size_t i = 0; i < wave_items.size(); ++i)
+                        fprintf(f, "%zu,%u,%u,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", i, wave_items[i].x, wave_items[i].y,
+                                (unsigned long long)Q.len(recs[wave_items[i].x].q), (unsigned long long)T.len(recs[wave_items[i].x].t),
+                                tr[4 * i], tr[4 * i + 1], tr[4 * i + 2] >> 8, tr[4 * i + 2] & 255, tr[4 * i + 3]);
+                    fclose(f);
+                }
+            }
         }
         TraceArgs ta;
         ta.Q = Q.dev(); ta.T = T.dev();

@@ -157,6 +157,7 @@ struct KArgs {
     int flip;
     uint4* wave_bnd;        // WAVE (two-row blocks): boundary columns as self-validating entries {H, epoch, E, epoch}
     uint32_t epoch;         // WAVE: this launch's tag (nonzero, never reused on this buffer)
+    unsigned long long* wave_trace;   // WAVE, diagnostics (BSA_WAVE_TRACE): per item {start ns, end ns, SM id, steps}, else null
 };
 
 __device__ __forceinline__ int max3_s32(int a, int b, int c) { return __vimax3_s32(a, b, c); }

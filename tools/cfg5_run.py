@@ -21,11 +21,13 @@ t = np.arange(1, 32, 2)
 with Context(0) as ctx:
     ctx.set_scoring("BLOSUM62", -10, -1)
     ctx.load_sequences(0, res, off)
-    for rep in range(2):
+    all_ms = []
+    for rep in range(int(os.environ.get("BSA_CFG5_REPS", "2"))):
         w0 = time.perf_counter()
         s, nid, paths = ctx.align_pairs_paths(0, 0, q, t)
         wall = time.perf_counter() - w0
         st = ctx.stats()
+        all_ms.append(round(st["kernel_ms"], 3))
 raw = res.tobytes()
 sc, ai = c_oracle.parse_ncbi(ncbi_text("BLOSUM62"))
 checked = []
@@ -39,5 +41,6 @@ for k in (() if os.environ.get("BSA_CFG5_NOCHECK") else (0, 1)):      # NOCHECK:
                     "path_len": len(paths[k]), "bit_exact": bool(ok), "oracle_seconds": time.perf_counter() - t0})
 print(json.dumps({"workload": "cfg5: 16 pairs, lengths %d..%d, full traceback" % (lens.min(), lens.max()),
                   "cells": st["cells"], "kernel_ms": st["kernel_ms"], "wall_ms": wall * 1e3,
-                  "GCUPS": st["cells"] / 1e6 / st["kernel_ms"], "checked_against_oracle": checked}))
+                  "GCUPS": st["cells"] / 1e6 / st["kernel_ms"], "kernel_ms_all_reps": all_ms,
+                  "checked_against_oracle": checked}))
 sys.exit(0 if all(c["bit_exact"] for c in checked) else 1)
