@@ -92,6 +92,9 @@ struct bsa_ctx {
     std::string err;
     cudaStream_t streams[kStreams] = {};
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_s[kStreams] = {};
+    cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;   // run_pairs_dirs: around the kernels of one batch
+    double dirs_kernel_ms = 0.0;                     // ... summed over the batches of the last call
+    int wave_attr_smem = -1, trace_attr_set = 0;    // cudaFuncSetAttribute done for these sizes
 
     // residue alphabet: one code per distinct raw byte ever loaded
     int code_of[256];
@@ -297,6 +300,7 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
                    const std::vector<uint64_t>* slot_off, std::vector<uint32_t>* path_len,
                    const std::vector<uint64_t>* req_index, LocalOut* d_lout = nullptr) {
     const bool local = d_lout != nullptr;   // LocalAlignment instead of GlobalAligner
+    ctx->dirs_kernel_ms = 0.0;
     if (reqs.empty()) return BSA_OK;
     const int C = std::max(ctx->ncodes, 1);
     // order by template so a CTA shares one profile between its warps
@@ -420,6 +424,32 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         CK(cudaMemsetAsync(ctx->status.p, 0, 4, st));
         ctx->stats.h2d_bytes += recs.size() * sizeof(PairRec) + sorted.size() * sizeof(Item);
 
+        // everything the host has to ask the runtime is asked before the first launch, so that the kernels of the
+        // batch run back to back and the two events around them time the device, not the host
+        const size_t wave_smem = wave_smem_bytes(wave_warps, C) + 1024;      // + slack to align the rings to 1 KB
+        if (!wave_items.empty() && ctx->wave_attr_smem != (int)wave_smem) {
+            CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, wave_smem));
+            if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "wavefront kernel does not fit on an SM");
+            ctx->wave_attr_smem = (int)wave_smem;
+        }
+        if (!local && !ctx->trace_attr_set) {
+            CK(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTraceWinLong)));
+            ctx->trace_attr_set = 1;
+        }
+        if (!wave_items.empty()) {
+            CK(ctx->wave_items.ensure(wave_items.size() * sizeof(uint2)));
+            CK(cudaMemcpyAsync(ctx->wave_items.p, wave_items.data(), wave_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+            const size_t need = std::max<uint64_t>(bnd_entries, 1) * sizeof(uint4);
+            if (need > ctx->wave_bnd.cap || ctx->wave_epoch == 0xfffffffeu) {
+                // the boundary buffer only ever holds {H, epoch, E, epoch} entries: zeroed when (re)allocated, epochs never repeat on it
+                CK(ctx->wave_bnd.ensure(need));
+                CK(cudaMemsetAsync(ctx->wave_bnd.p, 0, ctx->wave_bnd.cap, st));
+                ctx->wave_epoch = 0;
+            }
+        }
+        CK(cudaEventRecord(ctx->ev_d0, st));
         size_t gi = 0;
         int group = 0;
         while (gi < sorted.size()) {
@@ -455,8 +485,6 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             ++group;
         }
         if (!wave_items.empty()) {
-            CK(ctx->wave_items.ensure(wave_items.size() * sizeof(uint2)));
-            CK(cudaMemcpyAsync(ctx->wave_items.p, wave_items.data(), wave_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
             KArgs a;
             memset(&a, 0, sizeof(a));
             a.Q = Q.dev(); a.T = T.dev();
@@ -468,26 +496,13 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             a.pairs = ctx->pairs.as<PairRec>();
             a.dirs = ctx->dirs.as<uint32_t>();
             a.wave_items = ctx->wave_items.as<uint2>();
-            {
-                // the blocks hand their boundary columns over as {H, epoch, E, epoch} entries in a buffer that
-                // only ever holds such entries: zeroed when (re)allocated, epochs never repeat on it
-                const size_t need = std::max<uint64_t>(bnd_entries, 1) * sizeof(uint4);
-                if (need > ctx->wave_bnd.cap || ctx->wave_epoch == 0xfffffffeu) {
-                    CK(ctx->wave_bnd.ensure(need));
-                    CK(cudaMemsetAsync(ctx->wave_bnd.p, 0, ctx->wave_bnd.cap, st));
-                    ctx->wave_epoch = 0;
-                }
-                a.wave_bnd = ctx->wave_bnd.as<uint4>();
-                a.epoch = ++ctx->wave_epoch;
-            }
-            const size_t smem = wave_smem_bytes(wave_warps, C) + 1024;      // + slack to align the rings to 1 KB
-            CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, smem));
-            if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "wavefront kernel does not fit on an SM");
-            nb = 1;     // the wavefront is bound by its critical path: two warps per scheduler at most
+            a.wave_bnd = ctx->wave_bnd.as<uint4>();
+            a.epoch = ++ctx->wave_epoch;
+            const size_t smem = wave_smem;
+            const int nb = 1;     // the wavefront is bound by its critical path: two warps per scheduler at most
             // one CTA per SM, as many as there are items: the kernel deals the items out round-robin over the CTAs
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(wave_items.size(), (uint64_t)nb * ctx->sms);
+            uint32_t grid = (uint32_t)std::min<uint64_t>(wave_items.size(), (uint64_t)nb * ctx->sms);
+            if (const char* e = getenv("BSA_WAVE_GRID")) grid = std::max(1u, std::min(grid, (uint32_t)atoi(e)));   // diagnostics
             const char* trace_path = getenv("BSA_WAVE_TRACE");     // diagnostics: per-item start / end times
             unsigned long long* d_trace = nullptr;
             if (trace_path) {
@@ -533,11 +548,11 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             const uint32_t tb_warps = longp ? 1u : (uint32_t)kTraceMaxWarps;
             ta.win_bytes = longp ? kTraceWinLong : kTraceWinShort;
             const size_t tb_smem = (size_t)tb_warps * 2 * ta.win_bytes;
-            CK(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTraceWinLong)));
             const uint32_t tb_blocks = (ta.n_pairs + tb_warps - 1) / tb_warps;
             traceback_kernel<<<tb_blocks, tb_warps * 32, tb_smem, st>>>(ta);
         }
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_d1, st));
         ctx->stats.launches++;
         uint32_t status = 0;
         CK(cudaMemcpyAsync(&status, ctx->status.p, 4, cudaMemcpyDeviceToHost, st));
@@ -552,6 +567,11 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
             ctx->stats.d2h_bytes += recs.size() * 4 + path_bytes;
         }
         CK(cudaStreamSynchronize(st));
+        {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->ev_d0, ctx->ev_d1));
+            ctx->dirs_kernel_ms += ms;
+        }
         if (status) return fail(ctx, BSA_ERR_CUDA, "traceback met an invalid direction code");
         if (path_buf) {
             for (size_t i = 0; i < recs.size(); ++i) {
@@ -604,6 +624,8 @@ bsa_ctx* bsa_create(int device_id) {
     }
     cudaEventCreate(&c->ev_start);
     cudaEventCreate(&c->ev_end);
+    cudaEventCreate(&c->ev_d0);
+    cudaEventCreate(&c->ev_d1);
     register_kernels();
     if (cudaGetLastError() != cudaSuccess) { delete c; fail(nullptr, BSA_ERR_CUDA, "stream/event creation failed"); return nullptr; }
     return c;
@@ -627,6 +649,8 @@ void bsa_destroy(bsa_ctx* c) {
     }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_d0) cudaEventDestroy(c->ev_d0);
+    if (c->ev_d1) cudaEventDestroy(c->ev_d1);
     delete c;
 }
 
@@ -1569,9 +1593,8 @@ int bsa_align_pairs_paths(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_
     } else if (path_off) {
         for (uint64_t p = 0; p < n_pairs; ++p) path_off[p + 1] = 0;
     }
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));
-    ctx->stats.kernel_ms = ms;
+    // device time of the fill and traceback kernels, batch by batch (run_pairs_dirs); total_ms is the wall clock of the call
+    ctx->stats.kernel_ms = ctx->dirs_kernel_ms;
     ctx->stats.total_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     return BSA_OK;

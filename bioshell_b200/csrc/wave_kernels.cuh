@@ -50,6 +50,9 @@ namespace bsa {
 #ifndef BSA_WAVE_SLEEP_MAX
 #define BSA_WAVE_SLEEP_MAX 512  // ns: a block that waits for its left neighbour backs off up to this (a spinning warp takes issue slots from the working ones)
 #endif
+#ifndef BSA_WAVE_AFMA
+#define BSA_WAVE_AFMA 0       // {H source, E flag} accumulated with IMADs (7 ALU + 5 FMA per cell) instead of a funnel shift (8 + 3)
+#endif
 #ifndef BSA_WAVE_HIPRIO
 #define BSA_WAVE_HIPRIO 1     // first items (the longest pairs) start on the upper half of the warps of a CTA
 #endif
@@ -260,7 +263,12 @@ __device__ __forceinline__ int wave_block_frame(const uint8_t* __restrict__ qc, 
                 BSA_DIAG(hh[r] = max3_s32(dd[r], er[r], Fr[c]);)
                 BSA_DIAG(f1[r] = Fr[c] | 1;)
                 BSA_DIAG(hc[r] = hh[r] & ~7;)
+#if BSA_WAVE_AFMA
+                // {H source, E flag} on the FMA pipe: the low bits of h are h - hc, the word shifts by a multiplication
+                BSA_DIAG(dA[r] = dA[r] * 8u + bitsel((uint32_t)(hc[r] * mone + hh[r]), (uint32_t)er[r], notone);)
+#else
                 BSA_DIAG(dA[r] = __funnelshift_r(dA[r], bitsel((uint32_t)hh[r], (uint32_t)er[r], notone), 3);)
+#endif
                 BSA_DIAG(dF[r] = (uint32_t)(Fr[c] * mone + (int)(dF[r] * (uint32_t)two + (uint32_t)f1[r]));)   // 2 dF + (1 - m)
                 BSA_DIAG(er[r] = addmax_s32(hc[r], w.GOE, er[r] | 1);)
                 BSA_DIAG(Fr[c] = addmax_s32(hc[r], w.GOF, f1[r]);)
@@ -279,10 +287,12 @@ __device__ __forceinline__ int wave_block_frame(const uint8_t* __restrict__ qc, 
             oh[R - 1] = H[K - 1];
             {
                 uint4 wv;
-                wv.x = __byte_perm(dA[0], dF[0], 0x3214);
-                wv.y = __byte_perm(dA[1], dF[1], 0x3214);
-                wv.z = __byte_perm(dA[2], dF[2], 0x3214);
-                wv.w = __byte_perm(dA[3], dF[3], 0x3214);
+                // BSA_WAVE_AFMA: column c's 3 bits at 3 (7 - c), F flags in byte 3; else 3 bits at 8 + 3 c, F flags in byte 0
+                constexpr uint32_t SEL = BSA_WAVE_AFMA ? 0x4210u : 0x3214u;
+                wv.x = __byte_perm(dA[0], dF[0], SEL);
+                wv.y = __byte_perm(dA[1], dF[1], SEL);
+                wv.z = __byte_perm(dA[2], dF[2], SEL);
+                wv.w = __byte_perm(dA[3], dF[3], SEL);
                 *reinterpret_cast<uint4*>(dp) = wv;
                 dp += 512;
             }
@@ -553,10 +563,15 @@ __global__ void __launch_bounds__(kTraceMaxWarps * 32) traceback_kernel(const Tr
             const uint32_t wofs = line >= lo ? cb * WB + (line - lo) * LW + inner : (cb ^ 1u) * WB + (line - nlo) * LW + inner;
             const uint32_t wd = win0[wofs];
             if (frame) {
+#if BSA_WAVE_AFMA
+                const uint32_t a3 = (wd >> (3u * (7u - c))) & 7u;
+                fext = ((wd >> (31u - c)) & 1u) ^ 1u;
+#else
                 const uint32_t a3 = (wd >> (8u + 3u * c)) & 7u;
+                fext = ((wd >> (7u - c)) & 1u) ^ 1u;
+#endif
                 hdir = a3 >> 1;
                 eext = a3 & 1u;
-                fext = ((wd >> (7u - c)) & 1u) ^ 1u;
             } else {
                 const uint32_t left = K - 8u * (c >> 3);
                 const uint32_t cnt = left < 8u ? left : 8u;
