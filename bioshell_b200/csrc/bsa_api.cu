@@ -95,6 +95,7 @@ struct bsa_ctx {
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;   // run_pairs_dirs: around the kernels of one batch
     double dirs_kernel_ms = 0.0;                     // ... summed over the batches of the last call
     int wave_attr_smem = -1, trace_attr_set = 0;    // cudaFuncSetAttribute done for these sizes
+    std::mutex* gpu_gate = nullptr;   // child of a multi-device context: one tile's kernels at a time per GPU (planning and copies overlap)
 
     // residue alphabet: one code per distinct raw byte ever loaded
     int code_of[256];
@@ -838,6 +839,15 @@ int bsa_plan_shards(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_counts
     return BSA_OK;
 }
 
+// A child of a multi-device context holds its GPU's gate from its first launch until its kernels have finished:
+// the other child of that GPU plans its next tile meanwhile and copies its last results afterwards.
+struct GateGuard {
+    std::mutex* m = nullptr;
+    void lock(std::mutex* g) { if (g) { g->lock(); m = g; } }
+    void unlock() { if (m) { m->unlock(); m = nullptr; } }
+    ~GateGuard() { unlock(); }
+};
+
 int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_counts, uint32_t t_begin,
                         uint32_t t_end, uint32_t flags, int32_t* scores, uint32_t* n_identical,
                         uint64_t* n_results) {
@@ -1325,6 +1335,8 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         }
         if (scr_total) CK(ctx->scratch.ensure(scr_total * sizeof(uint2)));
     }
+    GateGuard gate;
+    gate.lock(ctx->gpu_gate);
     CK(cudaEventRecord(ctx->ev_start, s0));
     for (int i = 1; i < kStreams; ++i) CK(cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
     {
@@ -1470,6 +1482,10 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         ctx->stats.launches++;
     }
     CK(cudaEventRecord(ctx->ev_end, s0));
+    if (ctx->gpu_gate) {
+        CK(cudaEventSynchronize(ctx->ev_end));      // the kernels are through: the GPU is the next tile's
+        gate.unlock();
+    }
     if (!out_dev) {
         if (want_s) CK(cudaMemcpyAsync(scores, d_scores, n_res * 4, cudaMemcpyDeviceToHost, s0));
         if (want_i) CK(cudaMemcpyAsync(n_identical, d_nid, n_res * 4, cudaMemcpyDeviceToHost, s0));

@@ -2,15 +2,16 @@
 //
 // The reference's caller is a single process (bin/cluster_sequences.rs:173-177 calls align_all_pairs
 // once).  bsa_create_multi(device_ids, n_dev) returns a context whose entry points behave exactly
-// like a single-device context's, but which owns, per GPU, kWorkersPerGpu child contexts with one
-// host worker thread each:
+// like a single-device context's, but which owns, per GPU, one child context (BSA_MULTI_WORKERS_PER_GPU: up
+// to 4) with one host worker thread each:
 //   * sequence sets and scoring are replicated to every child (a set is a few MB to a few 100 MB);
-//   * bsa_align_all_pairs cuts the template range into cell-balanced TILES of decreasing size and the
-//     workers pull them from one atomic counter (dynamic balance over GPUs, no collective);
-//     every tile's results are copied by its child straight into the caller's buffer at the tile's
-//     own offset -- result k keeps its t-major position, so the bytes are identical for any number
-//     of GPUs -- and because each GPU has two children, one tile's device->host copy (true DMA when the
-//     buffer comes from bsa_host_alloc_pinned) overlaps the other child's kernels;
+//   * bsa_align_all_pairs cuts the template range into cell-balanced TILES -- by default one per GPU, each a
+//     complete single-device call -- that the workers pull from one atomic counter (no collective); every
+//     tile's results are copied by its child straight into the caller's buffer at the tile's own offset
+//     (true DMA when the buffer comes from bsa_host_alloc_pinned): result k keeps its t-major position, so
+//     the bytes are identical for any number of GPUs.  With two children per GPU the tiles are guided
+//     (decreasing sizes) and the children take turns on their GPU (gpu_gate), so that one tile's copy and
+//     the next tile's planning overlap the running tile's kernels;
 //   * pair lists (bsa_align_pairs_paths / bsa_local_align_pairs) are cut into contiguous chunks of
 //     equal cells, one per worker, and the paths are compacted back into pair order afterwards.
 // There is still no CPU alignment path: the workers only call the single-device entry points.
@@ -60,6 +61,7 @@ struct Worker {
 
 struct MultiState {
     std::vector<std::unique_ptr<Worker>> workers;
+    std::vector<std::unique_ptr<std::mutex>> gates;     // one per GPU
     int n_dev = 0;
     std::mutex stats_mu;
 
@@ -83,7 +85,7 @@ struct MultiState {
 
 namespace {
 
-constexpr int kWorkersPerGpuDefault = 2;
+constexpr int kWorkersPerGpuDefault = 1;
 
 void multi_add_stats(bsa_ctx* parent, const bsa_stats& s) {
     std::lock_guard<std::mutex> lk(parent->multi->stats_mu);
@@ -163,17 +165,31 @@ int multi_align_all_pairs(bsa_ctx* c, int q_set, int t_set, const uint32_t* q_co
     if (n_results) *n_results = first[nt];
     memset(&c->stats, 0, sizeof(c->stats));
     if (first[nt] == 0) return BSA_OK;
-    // guided tiles: each takes 1/(2 workers) of what is left, never less than kMinTile cells (a tile is a
-    // complete single-device call -- ~100 kernel groups -- so it must be worth ~0.1 s of one GPU)
+    // Tiles.  Default: ONE cell-balanced tile per GPU -- a tile is a complete single-device call (~100 kernel
+    // groups whose tails only overlap inside one call), the GPUs are identical, and a static split of the
+    // template range scales at 0.995 to 8 GPUs, so nothing is gained by cutting finer (measured: 6-7 guided
+    // tiles per GPU cost 14 % on cfg2).  With more than one worker per GPU (BSA_MULTI_WORKERS_PER_GPU=2)
+    // the tiles are guided instead -- each takes 1/(1.5 workers) of what is left, never less than kMinTile
+    // cells -- and the two children of a GPU take turns on it (bsa_ctx::gpu_gate): one tile's kernels run
+    // while the next tile is planned and the last one's results travel to the caller's buffer.
     const size_t nw = c->multi->workers.size();
+    const size_t n_gpu = (size_t)c->multi->n_dev;
     double kMinTile = 2.5e11;
     if (const char* e = getenv("BSA_MULTI_MIN_TILE")) kMinTile = std::max(1e6, atof(e));
     std::vector<uint32_t> cut{0};
-    {
+    if (nw == n_gpu) {
+        const double total = pre[nt];
+        for (size_t g = 1; g <= n_gpu && cut.back() < nt; ++g) {
+            size_t e = g == n_gpu ? nt : (size_t)(std::lower_bound(pre.begin(), pre.end(), total * (double)g / (double)n_gpu) - pre.begin());
+            e = std::min(std::max(e, (size_t)cut.back()), nt);
+            if (e > cut.back()) cut.push_back((uint32_t)e);
+        }
+        if (cut.back() < nt) cut.push_back((uint32_t)nt);
+    } else {
         double done = 0.0;
         const double total = pre[nt];
         while (cut.back() < nt) {
-            const double chunk = std::max((total - done) / (2.0 * (double)nw), kMinTile);
+            const double chunk = std::max((total - done) / (1.5 * (double)nw), kMinTile);
             size_t e = (size_t)(std::upper_bound(pre.begin(), pre.end(), done + chunk) - pre.begin());
             e = std::min(std::max(e, (size_t)cut.back() + 1), nt);     // at least one template
             if (total - pre[e] < kMinTile * 0.25) e = nt;             // no crumbs at the end
@@ -277,10 +293,13 @@ extern "C" bsa_ctx* bsa_create_multi(const int* device_ids, int n_dev) {
     c->multi = new MultiState();
     c->multi->n_dev = (int)ids.size();
     c->device = ids[0];
+    for (size_t g = 0; g < ids.size(); ++g) c->multi->gates.emplace_back(new std::mutex());
     for (int r = 0; r < per_gpu; ++r)           // worker order: one child per GPU first, then the second children
-        for (int d : ids) {
+        for (size_t g = 0; g < ids.size(); ++g) {
+            const int d = ids[g];
             bsa_ctx* kid = bsa_create(d);
             if (!kid) { multi_destroy(c); return nullptr; }   // bsa_create left the message
+            if (per_gpu > 1) kid->gpu_gate = c->multi->gates[g].get();
             std::unique_ptr<Worker> w(new Worker());
             w->kid = kid;
             Worker* wp = w.get();
