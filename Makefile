@@ -5,7 +5,7 @@ CXX       ?= g++
 NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -cudart static
 PKG       := bioshell_b200
 LIB       := $(PKG)/libbioshell_align.so
-CSRC      := $(wildcard $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh) include/bioshell_align.h
+CSRC      := $(wildcard $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh $(PKG)/csrc/*.inl) include/bioshell_align.h
 
 .PHONY: all lib host oracle test clean
 all: lib host oracle
