@@ -14,7 +14,9 @@ lib: $(LIB)
 $(LIB): $(CSRC)
 	$(NVCC) $(NVCCFLAGS) -o $@ $(PKG)/csrc/bsa_api.cu
 
-host: $(PKG)/host/test_host_mirror $(PKG)/host/test_clustering_host
+host: $(PKG)/host/test_host_mirror $(PKG)/host/test_clustering_host $(PKG)/host/test_bucket_host
+$(PKG)/host/test_bucket_host: $(PKG)/host/test_bucket_host.cpp $(PKG)/host/bioshell_bucket.hpp $(PKG)/host/bioshell_seq.hpp $(LIB)
+	$(CXX) -std=c++17 -O2 -Wall -o $@ $< -L$(PKG) -lbioshell_align -Wl,-rpath,'$$ORIGIN/..'
 $(PKG)/host/test_clustering_host: $(PKG)/host/test_clustering_host.cpp $(PKG)/host/bioshell_clustering.hpp $(PKG)/host/bioshell_seq.hpp $(LIB)
 	$(CXX) -std=c++17 -O2 -Wall -o $@ $< -L$(PKG) -lbioshell_align -Wl,-rpath,'$$ORIGIN/..'
 $(PKG)/host/test_host_mirror: $(PKG)/host/test_host_mirror.cpp $(PKG)/host/bioshell_seq.hpp $(LIB)
@@ -27,5 +29,5 @@ test:
 	python -m pytest tests -q -m "not gpu"
 
 clean:
-	rm -f $(LIB) $(PKG)/host/test_host_mirror $(PKG)/host/test_clustering_host
+	rm -f $(LIB) $(PKG)/host/test_host_mirror $(PKG)/host/test_clustering_host $(PKG)/host/test_bucket_host
 	rm -rf oracle/_ref

@@ -57,16 +57,15 @@ ROOF = {
     "tag": dict(ops=6.0, which=8, mix="frame cell: VIMNMX3 + LOP3 + 2 VIADDMNMX + 2 IMAD"),
     # 16-bit packed score-only cell: 4 ALU-pipe instructions per TWO cells (gotoh_score16_kernel)
     "s16": dict(ops=2.0, which=6, mix="ALU-pipe instructions of the u16x2 cell against the VIADDMNMX.S16x2 rate"),
-    # direction-store cell (gotoh_wave_kernel / gotoh_dirs_kernel): the 8-op classic cell + 4 to pack the nibble
-    "dirs": dict(ops=12.0, which=0, mix="classic cell (3 LOP3 + VIMNMX3 + 2 VIADDMNMX + 2 IMAD) + 4 LOP3/SHF for the direction nibble, "
-                                        "against the classic-cell mix"),
+    # K3 direction-frame cell (gotoh_wave_kernel, round 2): 8 ALU-pipe (VIMNMX3, 4 LOP3, 2 VIADDMNMX, SHF) + 3 IMAD
+    "dirs": dict(ops=11.0, which=9, mix="K3 direction-frame cell: VIMNMX3 + 4 LOP3 + 2 VIADDMNMX + SHF + 3 IMAD"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
 # captures committed under profiles/ (quoted, not re-measured per run: counters need a profiler)
 TRAFFIC_QUOTED = {
-    "tag": dict(bytes=3426816, source="profiles/r1_ncu_summary_tag.md: gotoh_pair_kernel<20,TAG>, 36.96 ms launch of the cfg2 run"),
+    "tag": dict(bytes=3086080, source="profiles/r2_ncu_summary_k1.md: gotoh_pair_kernel<17,TAG>, 42.6 ms launch of the cfg2 run"),
     "s16": dict(bytes=None, source=None),
-    "dirs": dict(bytes=3360000000, source="profiles/r1_ncu_summary_wave_ring.md: gotoh_wave_kernel on cfg5, 3.36 GB of directions written"),
+    "dirs": dict(bytes=4381725952, source="profiles/r2_ncu_summary_wave_frame.md: gotoh_wave_kernel on cfg5, 4.20 GB of directions written + 0.18 GB read"),
 }
 
 

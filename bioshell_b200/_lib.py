@@ -17,7 +17,7 @@ ERRORS = {-1: "BAD_ARG", -2: "UNSUPPORTED_GAPS", -3: "RANGE", -4: "CUDA", -5: "O
 WANT_SCORE, WANT_IDENTICAL, OUT_DEVICE, IN_DEVICE = 1, 2, 4, 8
 
 # every symbol include/bioshell_align.h declares
-SYMBOLS = ["bsa_device_count", "bsa_create", "bsa_create_multi", "bsa_context_devices", "bsa_destroy", "bsa_last_error",
+SYMBOLS = ["bsa_device_count", "bsa_create", "bsa_create_multi", "bsa_context_devices", "bsa_destroy", "bsa_last_error", "bsa_gather_sequences",
            "bsa_parse_ncbi_matrix", "bsa_set_scoring", "bsa_load_sequences", "bsa_align_all_pairs",
            "bsa_all_vs_all", "bsa_one_vs_many", "bsa_plan_shards", "bsa_align_pairs_paths",
            "bsa_host_alloc_pinned", "bsa_host_free_pinned", "bsa_get_stats", "bsa_measure_int_peak",
@@ -67,6 +67,7 @@ def lib():
     L.bsa_parse_ncbi_matrix.argtypes = [C.c_char_p, C.c_size_t, vp, vp]
     L.bsa_set_scoring.argtypes = [vp, vp, vp, i32, i32]
     L.bsa_load_sequences.argtypes = [vp, C.c_int, vp, vp, u32]
+    L.bsa_gather_sequences.argtypes = [vp, C.c_int, C.c_int, vp, u32]
     L.bsa_align_all_pairs.argtypes = [vp, C.c_int, C.c_int, vp, u32, u32, u32, vp, vp, C.POINTER(u64)]
     L.bsa_all_vs_all.argtypes = [vp, C.c_int, u32, vp, vp]
     L.bsa_one_vs_many.argtypes = [vp, C.c_int, C.c_int, u32, vp, vp]

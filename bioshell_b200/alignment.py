@@ -80,6 +80,12 @@ class Context:
                                             _p(off), len(off) - 1))
         self._sets[int(set_id)] = (len(off) - 1, np.diff(off.astype(np.int64)))
 
+    def gather_sequences(self, src_set, dst_set, idx):
+        """bsa_gather_sequences: sequence idx[i] of `src_set` becomes sequence i of `dst_set`, on the device."""
+        ix = np.ascontiguousarray(idx, np.uint32)
+        self._ck(self._L.bsa_gather_sequences(self._h, int(src_set), int(dst_set), _p(ix), len(ix)))
+        self._sets[int(dst_set)] = (len(ix), self._sets[int(src_set)][1][ix.astype(np.int64)])
+
     def n_sequences(self, set_id):
         return self._sets[int(set_id)][0]
 

@@ -13,6 +13,11 @@ one candidate against all current representatives are taken first (host, cheap);
 ones that precede the first certain hit are aligned in ONE GPU batch (in blocks, stopping at the
 first block that contains a hit) and then scanned in the reference's order, so the resulting
 clustering is identical; only the `aligned` statistic can be larger than the reference's.
+A batch is one candidate (the template, columns) against a list of representatives (queries,
+rows): the representatives are gathered into a set of their own on the device
+(bsa_gather_sequences) and the batch runs on the forward score + identity kernels
+(bsa_align_all_pairs) -- no direction store, no traceback.  The compiled twin of this driver is
+bioshell_b200/host/bioshell_bucket.hpp.
 """
 import numpy as np
 
@@ -115,10 +120,22 @@ class BucketClustering:
         self.kmer_sets = [generate_kmers(s.as_u8(), self.word_size) for s in self.sequences]
         self.stats = dict(above_threshold=0, below_threshold=0, aligned=0)
         self._ctx = ctx or default_context()
-        self._ctx.set_scoring("BLOSUM62", -11, -1)                                     # :223,300
         res, off = pack(self.sequences)
-        self._ctx.load_sequences(6, res, off)
+        self._ctx.load_sequences(self.SET_ALL, res, off)
         self._lens = lens
+
+    # sets of the context this driver uses: all sequences, the gathered representatives, the candidate
+    SET_ALL, SET_REPS, SET_CAND = 6, 7, 5
+
+    def _identical(self, reps, cand):
+        """n_identical of GlobalAligner(BLOSUM62, -11, -1) for query = each representative (rows) against
+        template = the candidate (columns), :296-300, on the forward kernels."""
+        ctx = self._ctx
+        ctx.set_scoring("BLOSUM62", -11, -1)        # :223,300 -- the context may have been used by others since
+        ctx.gather_sequences(self.SET_ALL, self.SET_REPS, reps)
+        ctx.gather_sequences(self.SET_ALL, self.SET_CAND, [cand])
+        _, nid = ctx.align_all_pairs(self.SET_REPS, self.SET_CAND, want_score=False)
+        return nid
 
     def run(self):
         """bucket_clustering.rs:162-169"""
@@ -177,7 +194,7 @@ class BucketClustering:
                 if pending:
                     reps = [clusters1[p].representative for p in pending]
                     # query = representative (rows), template = candidate (columns): :296-300
-                    _, nid, _ = self._ctx.align_pairs_paths(6, 6, reps, [cand] * len(reps), want_paths=False)
+                    nid = self._identical(reps, cand)
                     self.stats["aligned"] += len(reps)
                     for p, n_identical in zip(pending, nid):
                         shorter = np.float32(min(self._lens[cand], self._lens[clusters1[p].representative]))

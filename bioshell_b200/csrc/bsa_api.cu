@@ -114,7 +114,7 @@ struct bsa_ctx {
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
         raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair,
-        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC, wave_bnd;
+        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC, wave_bnd, gidx;
     bsa_stats stats;
     uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
     uint32_t wave_epoch = 0;    // tag of the last wavefront launch on wave_bnd
@@ -642,7 +642,7 @@ void bsa_destroy(bsa_ctx* c) {
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
                       &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair,
                       &c->lt_codes, &c->lt_off, &c->lt_idx, &c->lq_codes, &c->lq_off, &c->lq_idx, &c->lutB, &c->lutC,
-                      &c->wave_bnd};
+                      &c->wave_bnd, &c->gidx};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -813,6 +813,49 @@ int bsa_load_sequences(bsa_ctx* ctx, int set_id, const uint8_t* residues_raw, co
     }
     CK(cudaStreamSynchronize(st));
     S.loaded = true;
+    return BSA_OK;
+}
+
+int bsa_gather_sequences(bsa_ctx* ctx, int src_set, int dst_set, const uint32_t* idx, uint32_t n) {
+    if (!ctx) return BSA_ERR_BAD_ARG;
+    if (ctx->multi) return multi_gather_sequences(ctx, src_set, dst_set, idx, n);
+    if (src_set < 0 || src_set >= kMaxSets || dst_set < 0 || dst_set >= kMaxSets || src_set == dst_set || !idx)
+        return fail(ctx, BSA_ERR_BAD_ARG, "bad set id or null index list");
+    if (n == 0) return fail(ctx, BSA_ERR_EMPTY, "empty sequence set");
+    const SeqSet& S = ctx->sets[src_set];
+    if (!S.loaded) return fail(ctx, BSA_ERR_EMPTY, "sequence set not loaded");
+    for (uint32_t i = 0; i < n; ++i)
+        if (idx[i] >= S.n) return fail(ctx, BSA_ERR_BAD_ARG, "sequence index out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->streams[0];
+    SeqSet& D = ctx->sets[dst_set];
+    D.loaded = false;
+    D.n = n;
+    D.off.assign((size_t)n + 1, 0);
+    D.maxlen = 0;
+    D.empties.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t l = S.len(idx[i]);
+        D.off[i + 1] = D.off[i] + l;
+        D.maxlen = std::max(D.maxlen, l);
+        if (l == 0) D.empties.push_back(i);
+    }
+    D.total = D.off[n];
+    CK(D.codes.ensure(kFrontPad + D.total + kBackPad));
+    CK(D.doff.ensure(((size_t)n + 1) * 8));
+    CK(ctx->gidx.ensure((size_t)n * 4));
+    CK(cudaMemcpyAsync(D.doff.p, D.off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->gidx.p, idx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    ctx->pending_h2d += ((size_t)n + 1) * 8 + (size_t)n * 4;
+    // pads as in bsa_load_sequences; the residues never leave the device and keep their codes and last-residue flags
+    CK(cudaMemsetAsync(D.codes.p, 0, kFrontPad, st));
+    CK(cudaMemsetAsync(D.codes.as<uint8_t>() + kFrontPad - 1, (int)kLastFlag, 1, st));
+    CK(cudaMemsetAsync(D.codes.as<uint8_t>() + kFrontPad + D.total, 0, kBackPad, st));
+    gather_seqs_kernel<<<n, 128, 0, st>>>(S.dev(), ctx->gidx.as<uint32_t>(), D.doff.as<uint64_t>(),
+                                         D.codes.as<uint8_t>() + kFrontPad);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));      // idx is the caller's
+    D.loaded = true;
     return BSA_OK;
 }
 

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int on
         c[i] = seed - i - 3 * threadIdx.x;
     }
     const int ge = seed | 1, go = seed + 3, mask = ~(3 << 12), ph = 2 << 12, pv = 1 << 12;
+    unsigned dirA[2] = {(unsigned)seed, 0u}, dirF[2] = {0u, (unsigned)seed};   // WHICH == 9: direction accumulators
     unsigned long long c0 = 0, t0 = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -60,6 +61,19 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int on
                 a[i] = __viaddmax_s32(a[i], ge, hc * one2 + go);
                 b[i] = __viaddmax_s32(hc, ph, b[i]);
                 c[i] = hc;
+            } else if (WHICH == 9) {
+                // the K3 direction-frame cell (wave_kernels.cuh): VIMNMX3 + 4 LOP3 + 2 VIADDMNMX + SHF (ALU pipe) + 3 IMAD
+                const int d = c[i] * one + ge;
+                const int h = __vimax3_s32(d, a[i], b[i]);
+                unsigned x;
+                asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(x) : "r"(h), "r"(a[i]), "r"(mask));
+                dirA[i & 1] = __funnelshift_r(dirA[i & 1], x, 3);
+                const int f1 = b[i] | 1;
+                dirF[i & 1] = (unsigned)(b[i] * one2 + (int)(dirF[i & 1] * (unsigned)go + (unsigned)f1));
+                const int hc = h & ~7;
+                a[i] = __viaddmax_s32(hc, ph, a[i] | 1);
+                b[i] = __viaddmax_s32(hc, pv, f1);
+                c[i] = hc;
             } else if (WHICH == 1) {
                 a[i] = __viaddmax_s32(a[i], ge, b[i]);
             } else if (WHICH == 2) {
@@ -85,6 +99,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int on
     int s = 0;
 #pragma unroll
     for (int i = 0; i < kPeakChains; ++i) s += a[i] ^ b[i] ^ c[i];
+    if (WHICH == 9) s += (int)(dirA[0] ^ dirA[1] ^ dirF[0] ^ dirF[1]);
     if (s == 0x7fffffff) *sink = s;
 }
 
@@ -93,6 +108,7 @@ inline int peak_ops_per_iter(int which) {
         case 0: return 8;
         case 7: return 7;
         case 8: return 6;
+        case 9: return 11;
         case 2: return 2;   // VIMNMX3 + the LOP3 that perturbs it
         default: return 1;
     }
@@ -120,6 +136,7 @@ inline cudaError_t measure_int_peak(int which, int sms, cudaStream_t st, double*
             case 5: int_peak_kernel<5><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             case 7: int_peak_kernel<7><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             case 8: int_peak_kernel<8><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 9: int_peak_kernel<9><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
         }
     };

@@ -141,6 +141,23 @@ int multi_load_sequences(bsa_ctx* c, int set_id, const uint8_t* res, const uint6
     return BSA_OK;
 }
 
+int multi_gather_sequences(bsa_ctx* c, int src_set, int dst_set, const uint32_t* idx, uint32_t n) {
+    if (src_set < 0 || src_set >= kMaxSets || dst_set < 0 || dst_set >= kMaxSets || src_set == dst_set || !idx)
+        return fail(c, BSA_ERR_BAD_ARG, "bad set id or null index list");
+    const SeqSet& S = c->sets[src_set];
+    if (!S.loaded) return fail(c, BSA_ERR_EMPTY, "sequence set not loaded");
+    c->sets[dst_set].loaded = false;
+    const int rc = c->multi->run_all(c, [&](int, bsa_ctx* kid) { return bsa_gather_sequences(kid, src_set, dst_set, idx, n); });
+    if (rc) return rc;
+    SeqSet& D = c->sets[dst_set];      // host-side copy of the lengths: the parent plans the tiles
+    D.n = n;
+    D.off.assign((size_t)n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) D.off[i + 1] = D.off[i] + S.len(idx[i]);
+    D.total = D.off[n];
+    D.loaded = true;
+    return BSA_OK;
+}
+
 int multi_align_all_pairs(bsa_ctx* c, int q_set, int t_set, const uint32_t* q_counts, uint32_t t_begin,
                           uint32_t t_end, uint32_t flags, int32_t* scores, uint32_t* n_identical,
                           uint64_t* n_results) {

@@ -145,6 +145,17 @@ int bsa_one_vs_many(bsa_ctx *ctx, int q_set, int db_set, uint32_t flags, int32_t
                     uint32_t *n_identical);
 
 /*
+ * A new set from sequences of a loaded one, on the device: sequence idx[i] of src_set becomes
+ * sequence i of dst_set (indices may repeat; residues are not uploaded again).  This is how a
+ * pair list with a common template -- BucketClustering::sequence_identity of one candidate
+ * against the representatives whose k-mer bounds are inconclusive,
+ * bioshell-seq/src/sequence/bucket_clustering/bucket_clustering.rs:272-309 -- runs on the
+ * forward score + identity kernels: gather the representatives, gather the candidate, then
+ * bsa_align_all_pairs(gathered reps, {candidate}) (no direction store, no traceback).
+ */
+int bsa_gather_sequences(bsa_ctx *ctx, int src_set, int dst_set, const uint32_t *idx, uint32_t n);
+
+/*
  * Cell-balanced contiguous template ranges for n_shards GPUs/ranks:
  * bounds[0] = 0 <= ... <= bounds[n_shards] = |T|; shard r runs
  * bsa_align_all_pairs(..., bounds[r], bounds[r+1], ...).  No collective is needed.

@@ -1,8 +1,11 @@
 """Literal pure-Python restatement of bioshell-seq's bucket clustering (TEST INFRASTRUCTURE):
 bioshell-seq/src/sequence/bucket_clustering/{bucket_clustering.rs:141-309, kmers.rs:17-121}.
 One representative at a time, one alignment at a time (through the C oracle), exactly in the
-reference's order.  Parity status: UNPINNED by the reference (its two tests only run the
-function, tests/test_bucket_clustering.rs:36-62); pinned only against this restatement."""
+reference's order.  Parity status: the reference's two tests only run the function
+(tests/test_bucket_clustering.rs:36-62) and hold no expected output, so the pin is
+tests/golden/bucket_kats.json: clusterings of the reference's own test sequences derived from a
+table of (pinned-oracle) identities and a table of k-mer verdicts computed independently of this
+file (tools/gen_bucket_golden.py), both stored so that the expected clusters can be checked by hand."""
 import numpy as np
 
 from . import c_oracle
