@@ -274,6 +274,16 @@ def aligned_sequences(path, query, template, gap_symbol="-"):
 # ---------------------------------------------------------------------------
 # alignment_statistics.rs / alignment_reporter.rs / cluster_sequences.rs
 # ---------------------------------------------------------------------------
+def rust_fixed(x, width, prec):
+    """`{:width.prec}` of a Rust float: non-finite values print as NaN / inf / -inf (Python: nan)."""
+    x = float(x)
+    if x != x:
+        return "NaN".rjust(width)
+    if x in (float("inf"), float("-inf")):
+        return ("inf" if x > 0 else "-inf").rjust(width)
+    return "%*.*f" % (width, prec, x)
+
+
 class AlignmentStatistics:
     """alignment_statistics.rs:28-81.  `label_style` is a `sequence_id.LabelStyle`
     (sequence_label.rs:33-63); None keeps the raw descriptions (the batched path never builds
@@ -305,9 +315,9 @@ class AlignmentStatistics:
 
     def __str__(self):
         """alignment_statistics.rs:76-80"""
-        return "%s %s %6.2f %% %3d %4d %4d" % (self.query_header, self.template_header,
-                                               self.percent_identity(), self.n_identical,
-                                               self.query_length, self.template_length)
+        return "%s %s %s %% %3d %4d %4d" % (self.query_header, self.template_header,
+                                            rust_fixed(self.percent_identity(), 6, 2), self.n_identical,
+                                            self.query_length, self.template_length)
 
 
 class AlignmentReporter:
@@ -412,6 +422,8 @@ class PairResults:
 
     def percent_identity(self):
         """alignment_statistics.rs:71-73 in f64, then `as f32` (cluster_sequences.rs:128)."""
+        if self.n_identical is None:
+            raise ValueError("n_identical was not requested for this run (want_identical=False)")
         q, t = self.pair_indices()
         mn = np.minimum(self._lq[q], self._lt[t]).astype(np.float64)
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -452,9 +464,7 @@ def align_pairs_batched(queries, templates, matrix, gap_open, gap_extend, if_tri
     ctx, t_set, lq, lt = _prepare(ctx, queries, templates, matrix, gap_open, gap_extend)
     counts = triangle_counts(queries, templates, if_triangle_only)
     scores, nid = ctx.align_all_pairs(0, t_set, counts, want_identical=want_identical)
-    if nid is None:
-        nid = np.zeros(len(scores), np.uint32)
-    return PairResults(scores, nid, counts, lq, lt)
+    return PairResults(scores, nid, counts, lq, lt)      # nid stays None when it was not requested
 
 
 def align_all_pairs(queries, templates, matrix, gap_open, gap_extend, if_triangle_only, reporter,

@@ -19,6 +19,8 @@ import sys
 
 import numpy as np
 
+from .alignment import rust_fixed
+
 from . import _lib
 from .alignment import SequenceIdentityMatrix, align_all_vs_all, default_context
 from .sequence_id import LabelStyle, sequence_label
@@ -337,7 +339,7 @@ def cluster_sequences(sequences, linkage, gap_open=-10, gap_extend=-2, identity_
     if detect_outliers is not None:                                                      # :180-187
         d = dist.copy()
         np.fill_diagonal(d, np.finfo(np.float32).max)
-        out["outliers"] = [int(i) for i in np.nonzero(d.min(axis=1) > np.float32(100.0 - detect_outliers))[0]] \
+        out["outliers"] = [int(i) for i in np.nonzero(d.min(axis=1) > (np.float32(100.0) - np.float32(detect_outliers)))[0]] \
             if n >= 2 else []
         return out
     if linkage not in (single_link, complete_link, average_link):                       # :193-198
@@ -345,7 +347,7 @@ def cluster_sequences(sequences, linkage, gap_open=-10, gap_extend=-2, identity_
     clustering = hierarchical_clustering(n, dist, linkage, ctx)
     out["tree"] = clustering
     if identity_cutoff is not None:                                                      # :203-226
-        clusters = retrieve_clusters(clustering, np.float32(100.0 - identity_cutoff))
+        clusters = retrieve_clusters(clustering, (np.float32(100.0) - np.float32(identity_cutoff)))
         clusters.sort(key=lambda c: c.value.cluster_size)                                # stable, like sort_by
         out["clusters"] = [retrieve_data_id(c) for c in clusters]
         if write_files:
@@ -368,7 +370,7 @@ def cluster_sequences(sequences, linkage, gap_open=-10, gap_extend=-2, identity_
             labels = {i: sequence_label(sequences[i].description(), style) for i in seq_order}
             for k, i in enumerate(seq_order):
                 for l, j in enumerate(seq_order):
-                    fh.write("%s\t%s\t%6.3f\t%d\t%d\n" % (labels[i], labels[j], ident[i, j], k, l))
+                    fh.write("%s\t%s\t%s\t%d\t%d\n" % (labels[i], labels[j], rust_fixed(ident[i, j], 6, 3), k, l))
                 fh.write("\n")
     if fasta and write_files:                                                            # :251-256
         with open(fasta, "w") as fh:

@@ -83,11 +83,12 @@ bsa_ctx *bsa_create(int device_id);
  * bin/cluster_sequences.rs:173-177 calls align_all_pairs once).  n_dev == 0 takes
  * every visible device.  Every entry point below behaves as on a single-device context and
  * returns the same bytes: sequence sets and scoring are replicated to all devices; the library
- * runs one host worker thread per child context (two per GPU), cuts bsa_align_all_pairs /
- * bsa_all_vs_all / bsa_one_vs_many into cell-balanced template-range tiles that the workers pull
- * from a shared counter, and each tile's results are copied by its GPU straight into the caller's
- * output buffers at the tile's own t-major offset (true DMA, overlapped with the other child's
- * kernels, when the buffers come from bsa_host_alloc_pinned).  No collective, no NCCL.
+ * runs one host worker thread per GPU, cuts bsa_align_all_pairs / bsa_all_vs_all /
+ * bsa_one_vs_many into one cell-balanced template-range tile per GPU, and each tile's results are
+ * copied by its GPU straight into the caller's output buffers at the tile's own t-major offset
+ * (true DMA when the buffers come from bsa_host_alloc_pinned).  No collective, no NCCL.
+ * (BSA_MULTI_WORKERS_PER_GPU=2: guided tiles pulled from a shared counter, two children per GPU
+ * taking turns on it, so that one tile's copy and the next tile's planning overlap the kernels.)
  * Pair-list calls are split into contiguous chunks of equal cells.  BSA_OUT_DEVICE is refused.
  * bsa_hclust and bsa_measure_int_peak run on the first device.
  */

@@ -15,6 +15,8 @@ pub struct BsaCtx { _private: [u8; 0] }
 
 extern "C" {
     fn bsa_create(device_id: c_int) -> *mut BsaCtx;
+    fn bsa_create_multi(device_ids: *const c_int, n_dev: c_int) -> *mut BsaCtx;
+    fn bsa_gather_sequences(ctx: *mut BsaCtx, src_set: c_int, dst_set: c_int, idx: *const u32, n: u32) -> c_int;
     fn bsa_destroy(ctx: *mut BsaCtx);
     fn bsa_last_error(ctx: *const BsaCtx) -> *const c_char;
     fn bsa_set_scoring(ctx: *mut BsaCtx, score: *const i32, aa_index: *const u8, gap_open: i32, gap_extend: i32) -> c_int;
@@ -59,6 +61,22 @@ impl GpuAligner {
         Ok(GpuAligner { ctx })
     }
 
+    /// One context over every visible GPU (n_dev = 0) or the listed ones: the caller stays one process
+    /// (bin/cluster_sequences.rs:173-177) and every entry point returns the same bytes as on one device.
+    pub fn new_multi(devices: &[i32]) -> Result<Self, String> {
+        let ctx = unsafe { bsa_create_multi(devices.as_ptr(), devices.len() as c_int) };
+        if ctx.is_null() {
+            return Err(unsafe { CStr::from_ptr(bsa_last_error(std::ptr::null())) }.to_string_lossy().into());
+        }
+        Ok(GpuAligner { ctx })
+    }
+
+    /// Sequence idx[i] of `src_set` becomes sequence i of `dst_set`, on the device (bucket clustering's
+    /// candidate-vs-representatives batches, bucket_clustering.rs:272-309).
+    pub fn gather(&self, src_set: i32, dst_set: i32, idx: &[u32]) -> Result<(), String> {
+        self.check(unsafe { bsa_gather_sequences(self.ctx, src_set, dst_set, idx.as_ptr(), idx.len() as u32) })
+    }
+
     fn check(&self, rc: c_int) -> Result<(), String> {
         if rc == 0 { Ok(()) } else {
             Err(unsafe { CStr::from_ptr(bsa_last_error(self.ctx)) }.to_string_lossy().into())
@@ -76,11 +94,16 @@ impl GpuAligner {
     }
 
     /// The inner-loop trip count of alignment_protocols.rs:96-97 for every template.
+    /// `template == query` is `#[derive(PartialEq)]` on Sequence (description AND residues, sequence.rs:8);
+    /// the first query equal to each template is looked up in a hash map keyed by (description, residues)
+    /// -- one pass over the queries instead of a scan per template (5e9 compares at 100k sequences).
     fn triangle_counts(queries: &[Sequence], templates: &[Sequence], triangle: bool) -> Vec<u32> {
-        templates.iter().map(|t| {
-            if !triangle { return queries.len() as u32; }
-            queries.iter().position(|q| q == t).unwrap_or(queries.len()) as u32
-        }).collect()
+        if !triangle { return vec![queries.len() as u32; templates.len()]; }
+        let mut first: std::collections::HashMap<(&str, &[u8]), u32> = std::collections::HashMap::with_capacity(queries.len());
+        for (i, q) in queries.iter().enumerate() {
+            first.entry((q.description(), q.as_u8())).or_insert(i as u32);
+        }
+        templates.iter().map(|t| *first.get(&(t.description(), t.as_u8())).unwrap_or(&(queries.len() as u32))).collect()
     }
 
     /// Batched replacement of the `align_all_pairs` double loop: no strings are built.
