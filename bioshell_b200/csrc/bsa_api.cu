@@ -1759,8 +1759,8 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     const uint32_t grid = (uint32_t)ctx->sms * 8;
     const uint32_t pitch = (n + 31u) & ~31u;
     CK(ctx->hc_matrix.ensure((size_t)n * pitch * sizeof(float)));
-    // aux: rmap[n] sizes[n] order[2] mat_i[n] mat_j[n] mdist[n] result[n] partial[grid]
-    const size_t aux_bytes = (size_t)n * 4 * 6 + 16 + (size_t)grid * sizeof(HcBest) + 64;
+    // aux: rmap[n] sizes[n] mat_i[n] mat_j[n] mdist[n] result[n] rmin_v[n] rmin_j[n] todo[n] scalars[8] partial[grid]
+    const size_t aux_bytes = (size_t)n * 4 * 9 + 32 + (size_t)grid * sizeof(HcBest) + 64;
     CK(ctx->hc_aux.ensure(aux_bytes));
     HcState hs;
     hs.D = ctx->hc_matrix.as<float>();
@@ -1771,8 +1771,14 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     hs.mat_j = (uint32_t*)a; a += (size_t)n * 4;
     hs.mdist = (float*)a; a += (size_t)n * 4;
     hs.result = (float*)a; a += (size_t)n * 4;
-    hs.order = (uint32_t*)a; a += 16;
+    // nearest-neighbour cache (hclust_kernels.cuh): on unless BSA_HC_NN=0 asks for the full scan per merge
+    const bool use_nn = !(getenv("BSA_HC_NN") && atoi(getenv("BSA_HC_NN")) == 0);
+    hs.rmin_v = use_nn ? (float*)a : nullptr; a += (size_t)n * 4;
+    hs.rmin_j = use_nn ? (uint32_t*)a : nullptr; a += (size_t)n * 4;
+    hs.todo = (uint32_t*)a; a += (size_t)n * 4;
+    hs.order = (uint32_t*)a; a += 32;
     uint32_t* done_counter = hs.order + 2;
+    hs.todo_n = hs.order + 3;
     hs.partial = (HcBest*)a;
     hs.n = n;
     hs.pitch = pitch;
@@ -1788,6 +1794,13 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     hclust_init_kernel<<<grid, 256, 0, st>>>(hs, d_in);
     CK(cudaGetLastError());
     ctx->stats.launches++;
+    if (use_nn) {
+        hclust_rowmin_kernel<<<std::min<uint32_t>(n, (uint32_t)ctx->sms * 2), 1024, 0, st>>>(hs, 1);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+    }
+    const uint32_t nn_grid = std::max(1u, std::min(32u, (n + 2047u) / 2048u));     // cache entries: 12 bytes per row
+    const uint32_t redo_grid = 16;                                                 // rows i, j and the odd queued row
     uint32_t merge_grid = std::max(1u, std::min(24u, (n + 255u) / 256u));
     if (const char* e = getenv("BSA_HC_MERGE_GRID")) merge_grid = (uint32_t)std::max(1, atoi(e));   // debugging aid
     // Every merge is the same two launches with the same arguments (the state lives on the device),
@@ -1809,7 +1822,7 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
     uint32_t step = 0;
     while (step < n_merges && ge == cudaSuccess) {
         const uint32_t order = n - step;                 // rows alive before this merge
-        const int l = level_for(order);
+        const int l = use_nn ? 0 : level_for(order);          // the cache's grids do not depend on the order
         const uint32_t g = std::max(1u, grid >> l);
         if (use_graph && step + kHcGraphMerges <= n_merges) {
             if (!execs[l]) {
@@ -1817,8 +1830,14 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
                 ge = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
                 if (ge != cudaSuccess) break;
                 for (uint32_t k = 0; k < kHcGraphMerges; ++k) {
-                    hclust_argmin_kernel<<<g, 256, 0, st>>>(hs);
-                    hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, g, done_counter);
+                    if (use_nn) {
+                        hclust_nn_argmin_kernel<<<nn_grid, 256, 0, st>>>(hs);
+                        hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, nn_grid, done_counter);
+                        hclust_rowmin_kernel<<<redo_grid, 1024, 0, st>>>(hs, 0);
+                    } else {
+                        hclust_argmin_kernel<<<g, 256, 0, st>>>(hs);
+                        hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, g, done_counter);
+                    }
                 }
                 ge = cudaStreamEndCapture(st, &graph);
                 if (ge != cudaSuccess) break;
@@ -1827,8 +1846,14 @@ int bsa_hclust(bsa_ctx* ctx, uint32_t n, const float* dist, int linkage, uint32_
                 if (ge != cudaSuccess) break;
             }
             ge = cudaGraphLaunch(execs[l], st);
-            ctx->stats.launches += 2 * kHcGraphMerges;
+            ctx->stats.launches += (use_nn ? 3 : 2) * kHcGraphMerges;
             step += kHcGraphMerges;
+        } else if (use_nn) {
+            hclust_nn_argmin_kernel<<<nn_grid, 256, 0, st>>>(hs);
+            hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, nn_grid, done_counter);
+            hclust_rowmin_kernel<<<redo_grid, 1024, 0, st>>>(hs, 0);
+            ctx->stats.launches += 3;
+            ++step;
         } else {
             hclust_argmin_kernel<<<g, 256, 0, st>>>(hs);
             hclust_merge_kernel<<<merge_grid, 256, 0, st>>>(hs, g, done_counter);

@@ -110,3 +110,20 @@ def test_cluster_sequences_end_to_end(ctx, tmp_path, oracle_matrices):
     outl = cl.cluster_sequences(seqs, None, detect_outliers=35.0, ctx=ctx, write_files=False, reference_compat=False)
     dist = (f32(100.0) - np.maximum(ident, ident.T)).astype(f32)
     assert outl["outliers"] == pyhclust.retrieve_outliers(60, lambda i, j: dist[i, j], f32(65.0))
+
+
+def test_full_scan_mode_gives_the_same_logs(ctx, monkeypatch):
+    """BSA_HC_NN=0 rescans the whole triangle for every merge (round 1's path, the HBM-roofline kernel);
+    the default keeps a per-row nearest-neighbour cache.  Same merge logs, ties included."""
+    rng = np.random.default_rng(21)
+    for kind in ("ties", "identity_like"):
+        m = _matrix(rng, 300, kind)
+        for link, name in RULES:
+            got = cl.hclust_merge_log(300, m, link, ctx)
+            monkeypatch.setenv("BSA_HC_NN", "0")
+            full = cl.hclust_merge_log(300, m, link, ctx)
+            monkeypatch.delenv("BSA_HC_NN")
+            ref = c_oracle.hclust(m, name)
+            for a in (got, full):
+                assert np.array_equal(a[0], ref["mat_i"]) and np.array_equal(a[1], ref["mat_j"]), (kind, name)
+                assert np.array_equal(a[2].view(np.uint32), ref["dist"].view(np.uint32)), (kind, name)
