@@ -71,6 +71,17 @@ struct SeqSet {
     std::vector<uint32_t> empties;   // indices of zero-length sequences (ascending)
     DevBuf codes;                    // kFrontPad + total + kBackPad bytes
     DevBuf doff;                     // n+1 uint64
+    // even-aligned copy (a PAD byte ahead of every odd-length sequence), built on first use as the
+    // stream of the two-row kernels (ensure_aligned); invalidated whenever the set is loaded again
+    mutable DevBuf acodes, aoff;
+    mutable bool aligned = false;
+    SeqStoreDev adev() const {
+        SeqStoreDev d;
+        d.codes = acodes.as<uint8_t>() + kFrontPad;
+        d.off = aoff.as<uint64_t>();
+        d.n = n;
+        return d;
+    }
     SeqStoreDev dev() const {
         SeqStoreDev d;
         d.codes = codes.as<uint8_t>() + kFrontPad;
@@ -97,10 +108,11 @@ struct bsa_ctx {
     int wave_attr_smem = -1, trace_attr_set = 0;    // cudaFuncSetAttribute done for these sizes
     std::mutex* gpu_gate = nullptr;   // child of a multi-device context: one tile's kernels at a time per GPU (planning and copies overlap)
 
-    // residue alphabet: one code per distinct raw byte ever loaded
+    // residue alphabet: one code per distinct raw byte ever loaded; code 0 (kPadCode) is reserved for
+    // the PAD rows of the even-aligned stores and never stands for a residue
     int code_of[256];
     uint8_t byte_of[kMaxCodes];
-    int ncodes = 0;
+    int ncodes = 1;
 
     bool have_scoring = false;
     int32_t score[441];
@@ -114,7 +126,8 @@ struct bsa_ctx {
 
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
         raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair,
-        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC, wave_bnd, gidx;
+        lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC, wave_bnd, gidx,
+        lt_acodes, lt_aoff, lq_acodes, lq_aoff;
     bsa_stats stats;
     uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
     uint32_t wave_epoch = 0;    // tag of the last wavefront launch on wave_bnd
@@ -287,6 +300,38 @@ int sync_scoring(bsa_ctx* ctx) {
     CK(cudaMemcpy(ctx->d_subst.p, tab.data(), tab.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_isgap.p, gap.data(), gap.size(), cudaMemcpyHostToDevice));
     ctx->subst_codes = ctx->ncodes;
+    return BSA_OK;
+}
+
+// Even-aligned copy of a packed store for the two-row streaming kernels (gotoh_kernels.cuh,
+// stream_block_tag2a): every sequence starts at an even position and takes an even number of bytes,
+// an odd-length one behind a PAD byte (kPadCode); pads and the flagged byte ahead of sequence 0 as in
+// the store itself.  `off` = the host copy of the store's offsets.
+int build_aligned(bsa_ctx* ctx, const SeqStoreDev& src, const std::vector<uint64_t>& off, DevBuf& acodes,
+                  DevBuf& aoff, cudaStream_t st) {
+    const size_t n = off.size() - 1;
+    std::vector<uint64_t> ao(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) ao[i + 1] = ao[i] + ((off[i + 1] - off[i] + 1) & ~(uint64_t)1);
+    CK(acodes.ensure(kFrontPad + ao[n] + kBackPad));
+    CK(aoff.ensure((n + 1) * 8));
+    CK(cudaMemcpyAsync(aoff.p, ao.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(acodes.p, 0, kFrontPad, st));
+    CK(cudaMemsetAsync(acodes.as<uint8_t>() + kFrontPad - 1, (int)kLastFlag, 1, st));
+    CK(cudaMemsetAsync(acodes.as<uint8_t>() + kFrontPad + ao[n], 0, kBackPad, st));
+    if (n) {
+        align_seqs_kernel<<<(uint32_t)n, 128, 0, st>>>(src, aoff.as<uint64_t>(), acodes.as<uint8_t>() + kFrontPad);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+    }
+    ctx->stats.h2d_bytes += (n + 1) * 8;
+    CK(cudaStreamSynchronize(st));      // `ao` is a temporary
+    return BSA_OK;
+}
+int ensure_aligned(bsa_ctx* ctx, const SeqSet& S) {
+    if (S.aligned) return BSA_OK;
+    int rc = build_aligned(ctx, S.dev(), S.off, S.acodes, S.aoff, ctx->streams[0]);
+    if (rc) return rc;
+    S.aligned = true;
     return BSA_OK;
 }
 
@@ -618,6 +663,7 @@ bsa_ctx* bsa_create(int device_id) {
     c->device = device_id;
     c->sms = prop.multiProcessorCount;
     for (int i = 0; i < 256; ++i) c->code_of[i] = -1;
+    c->byte_of[kPadCode] = 0xff;   // byte 255 is never a residue (bsa_load_sequences refuses it)
     memset(&c->stats, 0, sizeof(c->stats));
     for (int i = 0; i < kStreams; ++i) {
         cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
@@ -637,12 +683,12 @@ void bsa_destroy(bsa_ctx* c) {
     if (c->multi) { multi_destroy(c); return; }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (auto& s : c->sets) { s.codes.release(); s.doff.release(); }
+    for (auto& s : c->sets) { s.codes.release(); s.doff.release(); s.acodes.release(); s.aoff.release(); }
     DevBuf* bufs[] = {&c->items, &c->counters, &c->scratch, &c->out_scores, &c->out_nid, &c->fixes,
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
                       &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair,
                       &c->lt_codes, &c->lt_off, &c->lt_idx, &c->lq_codes, &c->lq_off, &c->lq_idx, &c->lutB, &c->lutC,
-                      &c->wave_bnd, &c->gidx};
+                      &c->wave_bnd, &c->gidx, &c->lt_acodes, &c->lt_aoff, &c->lq_acodes, &c->lq_aoff};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -759,6 +805,7 @@ int bsa_load_sequences(bsa_ctx* ctx, int set_id, const uint8_t* residues_raw, co
     cudaStream_t st = ctx->streams[0];
     SeqSet& S = ctx->sets[set_id];
     S.loaded = false;
+    S.aligned = false;
     S.n = n;
     S.total = total;
     S.off.resize((size_t)n + 1);
@@ -792,7 +839,7 @@ int bsa_load_sequences(bsa_ctx* ctx, int set_id, const uint8_t* residues_raw, co
     if (pres[7] >> 31) return fail(ctx, BSA_ERR_ALPHABET, "residue byte 255 (the reference's [u8;255] lookup panics)");
     for (int b = 0; b < 255; ++b) {
         if (!((pres[b >> 5] >> (b & 31)) & 1u) || ctx->code_of[b] >= 0) continue;
-        if (ctx->ncodes >= kMaxCodes) return fail(ctx, BSA_ERR_ALPHABET, "more than 128 distinct residue byte values");
+        if (ctx->ncodes >= kMaxCodes) return fail(ctx, BSA_ERR_ALPHABET, "more than 127 distinct residue byte values");
         ctx->code_of[b] = ctx->ncodes;
         ctx->byte_of[ctx->ncodes++] = (uint8_t)b;
     }
@@ -830,6 +877,7 @@ int bsa_gather_sequences(bsa_ctx* ctx, int src_set, int dst_set, const uint32_t*
     cudaStream_t st = ctx->streams[0];
     SeqSet& D = ctx->sets[dst_set];
     D.loaded = false;
+    D.aligned = false;
     D.n = n;
     D.off.assign((size_t)n + 1, 0);
     D.maxlen = 0;
@@ -957,7 +1005,14 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_pad16, Q.maxlen);
             const int64_t lb = 5 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_pad16 + 68) * (int64_t)(-ctx->ge) +
                                (int64_t)std::max(-ctx->min_m, 0);
-            if (std::max(ub, lb) >= 32000) continue;
+            if (BSA_ALIGNED && !kc.multi) {
+                // single-block templates run in the moving frame score - (i + j) ge (stream_block16_fa): the frame
+                // adds up to (n + m) |ge| at the top; at the bottom nothing falls below three openings under a
+                // substitution score
+                const int64_t ubf = ub + (int64_t)(Q.maxlen + m_pad16 + 8) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+                const int64_t lbf = 4 * (int64_t)(ctx->ge - ctx->go) + 4 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
+                if (std::max(ubf, lbf) >= 32000) continue;
+            } else if (std::max(ub, lb) >= 32000) continue;
             cands.push_back(Cand{t, cnt, m, kc.K + (kc.multi ? kKMax + 1 : 0) + (int)kc.npass * 256});
         }
         // partners must agree on columns per lane, number of column blocks and query count
@@ -1024,6 +1079,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         uint64_t xmax = 0;                  // its longest sequence
         int cs_cap = 0;                     // count-field cap: bitlen(xmax)
         SeqStoreDev qdev, tdev;             // stream / owner store on the device
+        SeqStoreDev qadev;                  // even-aligned copy of the stream store (two-row TAG kernels)
         const uint64_t* lut = nullptr;      // device: result-index contribution per stream sequence
         int flip = 0;
         const char* name = "A";
@@ -1032,6 +1088,11 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     for (auto& V : var) { V.groups.resize(4 * kGroupStride); V.pairs.resize(2 * kGroupStride); }
     var[0].xoff = &Q.off; var[0].xmax = Q.maxlen; var[0].cs_cap = cs_cap;
     var[0].qdev = Q.dev(); var[0].tdev = T.dev();
+    if (BSA_ALIGNED) {
+        rc = ensure_aligned(ctx, Q);      // the two-row kernels (32-bit TAG and 16-bit frame) stream the aligned copy
+        if (rc) return rc;
+        var[0].qadev = Q.adev();
+    }
     var[1].name = "B"; var[1].flip = 1;
     var[2].name = "C";
 
@@ -1106,6 +1167,14 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         dT.codes = ctx->lt_codes.as<uint8_t>() + kFrontPad; dT.off = ctx->lt_off.as<uint64_t>(); dT.n = (uint32_t)lt.size();
         dQ.codes = ctx->lq_codes.as<uint8_t>() + kFrontPad; dQ.off = ctx->lq_off.as<uint64_t>(); dQ.n = (uint32_t)lq.size();
         var[1].xoff = &ltoff; var[1].xmax = mxT; var[1].cs_cap = bitlen(mxT);
+        if (use_tag) {
+            rc = build_aligned(ctx, dT, ltoff, ctx->lt_acodes, ctx->lt_aoff, ctx->streams[0]);
+            if (rc) return rc;
+            rc = build_aligned(ctx, dQ, lqoff, ctx->lq_acodes, ctx->lq_aoff, ctx->streams[0]);
+            if (rc) return rc;
+            var[1].qadev = SeqStoreDev{ctx->lt_acodes.as<uint8_t>() + kFrontPad, ctx->lt_aoff.as<uint64_t>(), dT.n};
+            var[2].qadev = SeqStoreDev{ctx->lq_acodes.as<uint8_t>() + kFrontPad, ctx->lq_aoff.as<uint64_t>(), dQ.n};
+        }
         var[1].qdev = dT; var[1].tdev = Q.dev(); var[1].lut = ctx->lutB.as<uint64_t>();
         var[2].xoff = &lqoff; var[2].xmax = mxQ; var[2].cs_cap = bitlen(mxQ);
         var[2].qdev = dQ; var[2].tdev = T.dev(); var[2].lut = ctx->lutC.as<uint64_t>();
@@ -1398,7 +1467,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 const Group& G = V.groups[L.g];
                 KArgs a;
                 memset(&a, 0, sizeof(a));
-                a.Q = V.qdev; a.T = V.tdev;
+                a.Q = V.qdev; a.T = V.tdev; a.QA = V.qadev;
                 a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
                 a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1;
                 a.items = ctx->items.as<Item>() + L.item_off;
@@ -1416,7 +1485,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 const KernelPairFn pfn = tag ? g_pair_tag[K] : g_pair[K];
                 KArgsPair a;
                 memset(&a, 0, sizeof(a));
-                a.Q = V.qdev; a.T = V.tdev;
+                a.Q = V.qdev; a.T = V.tdev; a.QA = V.qadev;
                 a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
                 a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1; a.cs_cap = V.cs_cap;
                 a.items = ctx->items_pair.as<Item16>() + L.item_off;
@@ -1474,6 +1543,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 KArgs16 a;
                 memset(&a, 0, sizeof(a));
                 a.Q = Q.dev(); a.T = T.dev();
+                a.QA = Q.adev();
                 a.subst = ctx->d_subst.as<int16_t>();
                 a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1;
                 a.items = ctx->items16.as<Item16>() + goff16[g];

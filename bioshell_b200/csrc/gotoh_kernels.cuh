@@ -44,7 +44,7 @@
 
 // tuning switches (tools/ab_build.sh builds variants of the library for same-box A/B runs)
 #ifndef BSA_TAG2_U
-#define BSA_TAG2_U 2        // double steps per loop iteration of the two-row blocks
+#define BSA_TAG2_U 4        // double steps per loop iteration of the two-row blocks (same-box A/B on cfg2: 2 -> 3195, 4 -> 3284, 8 -> 3024, 1 -> 3026 GCUPS)
 #endif
 #ifndef BSA_RING
 #define BSA_RING 0          // warp-wide prefetch (measured -0.4 % on cfg2: off) of the boundary column in multi-pass kernels
@@ -89,16 +89,24 @@
 #ifndef BSA_FLAG_SPLIT
 #define BSA_FLAG_SPLIT 0     // two-row blocks: a flagged double step whose flags all sit on its second row keeps the interleaved form
 #endif
+#ifndef BSA_ALIGNED
+#define BSA_ALIGNED 1       // two-row blocks read the EVEN-ALIGNED copy of the stream store (a PAD row ahead of odd-length
+                            // sequences): end-of-sequence flags only on the second row of a double step, one code path
+#endif
 #ifndef BSA_TWO_ROWS
 #define BSA_TWO_ROWS 1      // two-row step where TwoRows<K, HALF> says so
 #endif
 
 namespace bsa {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef BSA_WARPS_PER_CTA
+#define BSA_WARPS_PER_CTA 8
+#endif
+constexpr int kWarpsPerCta = BSA_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr uint32_t kLastFlag = 0x80u;  // set on the last residue of every sequence in the store
 constexpr uint32_t kCodeMask = 0x7Fu;
+constexpr uint32_t kPadCode = 0u;      // residue code 0 is never a residue: the PAD row of the even-aligned stores
 constexpr int kFrontPad = 64;          // bytes before the first sequence (last one flagged)
 constexpr int kBackPad = 128;          // bytes after the last sequence
 
@@ -130,6 +138,7 @@ struct SeqStoreDev {
 
 struct KArgs {
     SeqStoreDev Q, T;
+    SeqStoreDev QA;         // even-aligned copy of the stream store Q (two-row TAG blocks; see stream_block_tag2a)
     const int16_t* subst;   // C x C substitution scores by residue code
     const uint8_t* isgap;   // C flags: code is '-' or '_' (never identical, msa.rs:264)
     int C;
@@ -334,6 +343,9 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
                 const int tcode = tc[col] & kCodeMask;
                 val = ((int)subst[a.flip ? tcode * C + code : code * C + tcode] + cs.TSUB) * S + P3 +
                       ((cs.cs > 0 && tcode == code && !gap) ? 1 : 0);   // no count field when cs == 0
+                // frame cell: the PAD row adds nothing on the diagonal of the frame (go - ge in DP column 1,
+                // whose diagonal input is H*[0][0] = 0), so it reproduces the top border
+                if (cs.XTOP && code == (int)kPadCode) val = (col == 0 ? cs.hb0 : 0) + P3;
             }
             o[e] = val;
         }
@@ -370,6 +382,29 @@ __device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict_
         if (4 * v + 2 < K) dst[4 * v + 2] = (int)x.z;
         if (4 * v + 3 < K) dst[4 * v + 3] = (int)x.w;
     }
+}
+
+// The same load, opaque to the compiler: the border vectors a lane reloads when it passes the end of a
+// sequence are loop invariant, and hoisting them would pin 2 K registers for the whole DP loop.
+template <int K>
+__device__ __forceinline__ void load_vec_opaque(int (&dst)[K], const uint4* src) {
+    constexpr int V = KTraits<K>::V;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(src);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        int x, y, z, w;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr + (uint32_t)v * 512u));
+        if (4 * v + 0 < K) dst[4 * v + 0] = x;
+        if (4 * v + 1 < K) dst[4 * v + 1] = y;
+        if (4 * v + 2 < K) dst[4 * v + 2] = z;
+        if (4 * v + 3 < K) dst[4 * v + 3] = w;
+    }
+}
+// a value the compiler can neither rematerialise nor move into a uniform register
+__device__ __forceinline__ int opaque_reg(int v) {
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return v;
 }
 
 // Same row from a 16-bit profile: 8 entries per uint4, [code][v16][lane]; entry c of a lane sits in
@@ -902,6 +937,133 @@ _Pragma("unroll")                                                               
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Two rows per step over the EVEN-ALIGNED copy of the stream store (BSA_ALIGNED).  Every sequence
+// starts at an even stream position and takes an even number of bytes: an odd-length sequence is
+// preceded by one PAD row (residue code 0), whose profile row adds nothing on the diagonal of the
+// moving frame and therefore reproduces the top border (H* = go - ge, the stored F keep their top
+// tag bit; tests/packed_model.py::frame_align(pad=True) is the scalar model, checked against the
+// oracle).  The end-of-sequence flag then always sits on the SECOND row of a double step, so the
+// interleaved two-row body is the only form of the cell code: no sequential-row path, half the
+// code, and a flagged step costs the interleaved step plus the reset of the flagged lanes.
+// The one special case: the diagonal input of the first real row in DP column 1 is H*[0][0] = 0,
+// which lane 0 takes instead of the left border when the row above is the PAD row.
+// `qoffp` = the ORIGINAL offsets of the chunk's first sequence (the emitted score leaves the frame
+// with the real number of rows); the left border enters lane 0 without selects (IMAD / LOP3).
+template <int K, bool HALF>
+__device__ __forceinline__ void stream_block_tag2a(const uint8_t* __restrict__ codes, uint64_t g0, uint64_t g1,
+                                                   const uint4* prof, const uint4* rsH, const uint4* rsF,
+                                                   const int lane, const int lane_last, const int slot_last,
+                                                   const int hdiag0, const Consts cs, const int one, const int one2,
+                                                   int32_t* __restrict__ scores, uint32_t* __restrict__ nident,
+                                                   uint64_t out_idx0, const int m_emit,
+                                                   const uint64_t* __restrict__ lutp,
+                                                   const uint64_t* __restrict__ qoffp) {
+    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int U = BSA_TAG2_U;  // double steps per loop iteration
+    static_assert(8 % U == 0, "the stored F get the top tag bit every 8 double steps");
+    const uint32_t X = (uint32_t)(g1 - g0);        // even
+    const int span = HALF ? 15 : lane_last;
+    const uint32_t nd = (X / 2u + (uint32_t)span + (U - 1)) / U * U;
+    const int lrel = HALF ? (lane & 15) : lane;
+    const bool lane0 = lrel == 0;
+    // the constant left border of the frame, H*[i][0] = go - ge and E*[i][1], enters lane 0 as
+    // hin = shuffled * nl0 + hbl (IMAD) and er = (shuffled & keepx) | ebl (one LOP3, which also
+    // clears the streak field of the E that crossed the lane boundary)
+    const int nl0 = opaque_reg(lane0 ? 0 : one);
+    const int hbl = opaque_reg(lane0 ? cs.hb0 : 0);
+    const int ebl = opaque_reg(lane0 ? cs.hb0 + cs.GOE : 0);
+    const int keepx = opaque_reg(lane0 ? 0 : cs.XCLR);
+    const int one_a = opaque_reg(one), one_b = opaque_reg(one2);
+
+    int H[K], Fr[K], T0[K], T1[K];
+    load_vec<K>(H, rsH + lane);
+    load_vec<K>(Fr, rsF + lane);
+    int hdiag = hdiag0;
+    int cf = cs.GOF;                               // F opening addend of the first row of the current double step
+    int oh0 = 0, oe0 = 0, oh1 = 0, oe1 = 0;
+    uint32_t emitted = 0;
+    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
+    const uint8_t* p = codes + g0 - 2 * lrel;   // lane's first row at double step 0 (may sit in the padding)
+    uint32_t b[2 * U], nb[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) b[u] = ld_code(p + u);
+
+    for (uint32_t S = 0; S < nd; S += U) {
+        if ((S & 7u) == 0u) {
+            // a new block of 16 rows: what is stored outranks every opening of the block
+#pragma unroll
+            for (int c = 0; c < K; ++c) Fr[c] |= cs.XTOP;
+            cf = cs.GOF + (int)(kTagRows - 1u) * cs.X1;
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) nb[u] = ld_code(p + 2 * U + u);   // prefetch the next group's residues
+        p += 2 * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t b0 = b[2 * u], b1 = b[2 * u + 1];     // b0 never carries a flag
+            load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+            load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b1 & kCodeMask) * ROWB));
+            const int sh0 = __shfl_up_sync(0xffffffffu, oh0, 1);
+            const int se0 = __shfl_up_sync(0xffffffffu, oe0, 1);
+            const int sh1 = __shfl_up_sync(0xffffffffu, oh1, 1);
+            const int se1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+            // row 1's diagonal input in this lane's first column = row 0's H to the left; for lane 0 the
+            // border, or H*[0][0] = 0 when row 0 is the PAD row
+            const int hin0 = sh0 * nl0 + (b0 == kPadCode ? 0 : hbl);
+            const int hin1 = sh1 * nl0 + hbl;
+            int er0 = (se0 & keepx) | ebl;
+            int er1 = (se1 & keepx) | ebl;
+            const int cf0 = cf, cf1 = cf - cs.X1;
+            cf -= 2 * cs.X1;
+            int hd0 = hdiag, hd1 = hin0;
+            hdiag = hin1;
+            int hc1 = 0;
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+                const int d0 = hd0 * one_a + T0[c];
+                const int h0 = max3_s32(d0, er0, Fr[c]);
+                const int hc0 = h0 & cs.MASK;
+                er0 = addmax_s32(er0, cs.X1, hc0 * one_a + cs.GOE);
+                const int f1 = addmax_s32(hc0, cf0, Fr[c]);
+                hd0 = H[c];
+                const int d1 = hd1 * one_b + T1[c];
+                const int h1 = max3_s32(d1, er1, f1);
+                hc1 = h1 & cs.MASK;
+                er1 = addmax_s32(er1, cs.X1, hc1 * one_b + cs.GOE);
+                Fr[c] = addmax_s32(hc1, cf1, f1);
+                hd1 = hc0;
+                H[c] = hc1;
+            }
+            oh0 = hd1;
+            oe0 = er0;
+            oh1 = hc1;
+            oe1 = er1;
+            if (b1 & kLastFlag) {
+                // this lane has finished a sequence: emit (the lane that owns the last column), back to the top border
+                const uint32_t pos1 = 2u * (S + u - (uint32_t)lrel) + 1u;   // wraps below row 0: fails pos1 < X
+                const bool valid = pos1 < X;
+                if (valid && lane == lane_last) {
+                    int v = 0;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) if (c == slot_last) v = H[c];
+                    const uint32_t n = (uint32_t)(qoffp[emitted + 1] - qoffp[emitted]);
+                    const uint64_t k = out_idx0 + (lutp ? lutp[emitted] : (uint64_t)emitted);
+                    // out of the frame: H = H* + (n + m) ge, n = rows of this sequence
+                    if (scores) scores[k] = (v >> cs.sh) + (int)(n + (uint32_t)m_emit) * cs.ge;
+                    if (nident) nident[k] = (uint32_t)v & ((1u << cs.cs) - 1u);
+                }
+                emitted += valid ? 1u : 0u;
+                load_vec_opaque<K>(H, rsH + lane);
+                load_vec_opaque<K>(Fr, rsF + lane);
+                hdiag = hdiag0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) b[u] = nb[u];
+    }
+}
+
 __device__ __forceinline__ uint32_t lower_bound_off(const uint64_t* __restrict__ off, uint32_t lo,
                                                     uint32_t hi, uint64_t x) {
     // first index i in [lo, hi] with off[i] >= x
@@ -979,7 +1141,10 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
 
         // chunk schedule: big chunks over the first 13/16 of the stream, small ones over the rest,
         // so the warps reach the item's closing barrier within half a small chunk of each other
-        const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
+        // the two-row TAG blocks stream the even-aligned copy of the store (chunks are whole sequences either way)
+        constexpr bool kAligned = BSA_ALIGNED && TAG && !MULTI && TwoRows<K, false>::value;
+        const uint64_t* __restrict__ xoff = kAligned ? a.QA.off : a.Q.off;
+        const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
         const uint64_t span = x1 - x0;
         const uint64_t head = span - span * 3 / 16;
         const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
@@ -1020,12 +1185,17 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
                 const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
                 const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig
                                                   : head + (span - head) * (c + 1 - nbig) / nsmall;
-                const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
+                const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + ca);
                 const uint32_t qb = c + 1 == nch ? it.q_end
-                                                 : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
-                const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+                                                 : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + cb);
+                const uint64_t g0 = xoff[qa], g1 = xoff[qb];
                 if (g1 <= g0) continue;
-                if constexpr (TAG && !MULTI && TwoRows<K, false>::value)
+                if constexpr (kAligned)
+                    stream_block_tag2a<K, false>(a.QA.codes, g0, g1, prof, rsH, rsF, lane, lane_last, slot_last,
+                                                 hdiag0, cs, a.one, a.one2, a.scores, a.nident,
+                                                 a.out_lut ? it.out_base : it.out_base + (qa - it.q_begin), (int)m,
+                                                 a.out_lut ? a.out_lut + qa : nullptr, a.Q.off + qa);
+                else if constexpr (TAG && !MULTI && TwoRows<K, false>::value)
                     stream_block_tag2<K, false>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, lane_last, slot_last,
                                                 hdiag0, cs, a.one, a.one2, a.scores, a.nident,
                                                 a.out_lut ? it.out_base : it.out_base + (qa - it.q_begin), (int)m,
@@ -1115,6 +1285,7 @@ __global__ void __launch_bounds__(kThreads) gotoh_dirs_kernel(const KArgs a) {
 // 2K cells instead of once per K, and the column padding is cut to a 16-column granularity.
 struct KArgsPair {
     SeqStoreDev Q, T;
+    SeqStoreDev QA;         // even-aligned copy of the stream store (see KArgs)
     const int16_t* subst;
     const uint8_t* isgap;
     int C, go, ge, one, one2;
@@ -1443,6 +1614,121 @@ _Pragma("unroll")                                                               
 #undef BSA_PAIR16
 }
 
+// ---------------------------------------------------------------------------------------------
+// Score only, 16-bit packed lanes, in the MOVING FRAME over the EVEN-ALIGNED stream (BSA_ALIGNED;
+// single-block templates).  Every stored value of cell (i, j) is score - (i + j) * gap_extend, so
+// both gap extensions are free and the cell is FOUR instructions per TWO cells, all of them DPX:
+//     t = max(hdiag + T, e)            VIADDMNMX.U16x2     (T = s - 2 ge)
+//     h = max(t, f)                    VIMNMX.U16x2
+//     e = max(h + (go - ge), e)        VIADDMNMX.U16x2
+//     f = max(h + (go - ge), f)        VIADDMNMX.U16x2
+// The borders are the constants go - ge (H*) and 2 (go - ge) (the eager E* / F*), so there is no
+// border arithmetic per row and the reset of a lane that passes the end of a sequence is a set of
+// register moves.  Odd-length sequences are preceded by a PAD row (stream_block_tag2a explains the
+// aligned stream): its profile row is 0 (go - ge in DP column 1) and reproduces the top border, so
+// the end-of-sequence flag always sits on the second row of a double step and the interleaved
+// two-row body is the only form of the cell code.  Values stay biased by 0x8000 per half.
+// The score leaves the frame when it is emitted: H = H* + (n + m) ge with the sequence's real length.
+template <int K>
+__device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ codes, uint64_t g0, uint64_t g1,
+                                                  const uint4* prof, const int lane, const int lastA,
+                                                  const int slotA, const int lastB, const int slotB,
+                                                  const uint32_t hdiag0, const uint32_t HB, const uint32_t GOF2,
+                                                  const int ge, const int mA, const int mB,
+                                                  int32_t* __restrict__ scores, uint64_t outA, uint64_t outB,
+                                                  const uint64_t* __restrict__ qoffp) {
+    constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
+    constexpr int U = BSA_TAG2_U;
+    const uint32_t X = (uint32_t)(g1 - g0);        // even
+    const int span = lastA > lastB ? lastA : lastB;
+    const uint32_t nd = (X / 2u + (uint32_t)span + (U - 1)) / U * U;
+    const bool lane0 = lane == 0;
+    const uint32_t FB = add2(HB, GOF2);            // eager E*[i][1] and F*[1][j]: opened from the border
+    // the constant left border enters lane 0 through one LOP3 per value: (shuffled & keep) | border
+    const uint32_t keep = (uint32_t)opaque_reg(lane0 ? 0 : -1);
+    const uint32_t hbl = (uint32_t)opaque_reg(lane0 ? (int)HB : 0);
+    const uint32_t zbl = (uint32_t)opaque_reg(lane0 ? (int)kBias2 : 0);   // H*[0][0] = 0: the row above is the PAD row
+    const uint32_t ebl = (uint32_t)opaque_reg(lane0 ? (int)FB : 0);
+
+    uint32_t H[K], Fr[K];
+    int T0[K], T1[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) { H[c] = HB; Fr[c] = FB; }
+    uint32_t hdiag = hdiag0;
+    uint32_t oh0 = 0, oe0 = 0, oh1 = 0, oe1 = 0, emitted = 0;
+    const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
+    const uint8_t* p = codes + g0 - 2 * lane;
+    uint32_t b[2 * U], nb[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) b[u] = ld_code(p + u);
+
+    for (uint32_t S = 0; S < nd; S += U) {
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) nb[u] = ld_code(p + 2 * U + u);
+        p += 2 * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t b0 = b[2 * u], b1 = b[2 * u + 1];     // b0 never carries a flag
+            load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+            load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b1 & kCodeMask) * ROWB));
+            const uint32_t sh0 = __shfl_up_sync(0xffffffffu, oh0, 1);
+            const uint32_t se0 = __shfl_up_sync(0xffffffffu, oe0, 1);
+            const uint32_t sh1 = __shfl_up_sync(0xffffffffu, oh1, 1);
+            const uint32_t se1 = __shfl_up_sync(0xffffffffu, oe1, 1);
+            const uint32_t hin0 = (sh0 & keep) | (b0 == kPadCode ? zbl : hbl);
+            const uint32_t hin1 = (sh1 & keep) | hbl;
+            uint32_t e0 = (se0 & keep) | ebl;
+            uint32_t e1 = (se1 & keep) | ebl;
+            uint32_t hd0 = hdiag, hd1 = hin0, h1 = 0;
+            hdiag = hin1;
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+                const uint32_t t0 = __viaddmax_u16x2(hd0, (uint32_t)T0[c], e0);
+                const uint32_t h0 = __vmaxu2(t0, Fr[c]);
+                e0 = __viaddmax_u16x2(h0, GOF2, e0);
+                const uint32_t f1 = __viaddmax_u16x2(h0, GOF2, Fr[c]);
+                hd0 = H[c];
+                const uint32_t t1 = __viaddmax_u16x2(hd1, (uint32_t)T1[c], e1);
+                h1 = __vmaxu2(t1, f1);
+                e1 = __viaddmax_u16x2(h1, GOF2, e1);
+                Fr[c] = __viaddmax_u16x2(h1, GOF2, f1);
+                hd1 = h0;
+                H[c] = h1;
+            }
+            oh0 = hd1;
+            oe0 = e0;
+            oh1 = h1;
+            oe1 = e1;
+            if (b1 & kLastFlag) {
+                const uint32_t pos1 = 2u * (S + u - (uint32_t)lane) + 1u;   // wraps below row 0: fails pos1 < X
+                const bool valid = pos1 < X;
+                if (valid && scores && (lane == lastA || lane == lastB)) {
+                    const int n = (int)(qoffp[emitted + 1] - qoffp[emitted]);
+                    if (lane == lastA) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int c = 0; c < K; ++c) if (c == slotA) v = H[c];
+                        scores[outA + emitted] = (int)(v & 0xffffu) - 0x8000 + (n + mA) * ge;
+                    }
+                    if (lane == lastB) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int c = 0; c < K; ++c) if (c == slotB) v = H[c];
+                        scores[outB + emitted] = (int)(v >> 16) - 0x8000 + (n + mB) * ge;
+                    }
+                }
+                emitted += valid ? 1u : 0u;
+                const uint32_t hbr = (uint32_t)opaque_reg((int)HB), fbr = (uint32_t)opaque_reg((int)FB);
+#pragma unroll
+                for (int c = 0; c < K; ++c) { H[c] = hbr; Fr[c] = fbr; }
+                hdiag = hdiag0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * U; ++u) b[u] = nb[u];
+    }
+}
+
 template <int K, bool TAG = false>
 __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kernel(const KArgsPair a) {
     extern __shared__ uint4 smem[];
@@ -1474,7 +1760,9 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const Consts cs = make_consts<K>(a.go, a.ge, cshift, false, TAG, a.flip != 0);
         const int S = 1 << cs.sh, P3 = 3 << cs.ps;
 
-        const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
+        constexpr bool kAligned = BSA_ALIGNED && TAG && TwoRows<K, true>::value;
+        const uint64_t* __restrict__ xoff = kAligned ? a.QA.off : a.Q.off;
+        const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
         const uint64_t span = x1 - x0;
         const uint64_t head = span - span * 3 / 16;
         const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
@@ -1512,6 +1800,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
                     const int tcode = tc[col] & kCodeMask;
                     val = ((int)s_subst[a.flip ? tcode * a.C + code : code * a.C + tcode] + cs.TSUB) * S + P3 +
                           ((tcode == code && !gap) ? 1 : 0);
+                    if (TAG && code == (int)kPadCode) val = (col == 0 ? cs.hb0 : 0) + P3;   // PAD row, see build_profile
                 }
                 o[e] = val;
             }
@@ -1544,11 +1833,16 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
             if (c >= nch) break;
             const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
             const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig : head + (span - head) * (c + 1 - nbig) / nsmall;
-            const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
-            const uint32_t qb = c + 1 == nch ? it.q_end : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
-            const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+            const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + ca);
+            const uint32_t qb = c + 1 == nch ? it.q_end : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + cb);
+            const uint64_t g0 = xoff[qa], g1 = xoff[qb];
             if (g1 <= g0) continue;
-            if constexpr (TAG && TwoRows<K, true>::value)
+            if constexpr (kAligned)
+                stream_block_tag2a<K, true>(a.QA.codes, g0, g1, prof, rsH, rsF, lane, my_last, my_slot, hdiag0, cs,
+                                            a.one, a.one2, a.scores, a.nident,
+                                            (isB ? it.outB : it.outA) + (a.out_lut ? 0 : qa - it.q_begin), (int)mine,
+                                            a.out_lut ? a.out_lut + qa : nullptr, a.Q.off + qa);
+            else if constexpr (TAG && TwoRows<K, true>::value)
                 stream_block_tag2<K, true>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, my_last, my_slot, hdiag0, cs,
                                            a.one, a.one2, a.scores, a.nident,
                                            (isB ? it.outB : it.outA) + (a.out_lut ? 0 : qa - it.q_begin), (int)mine,
@@ -1564,6 +1858,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
 
 struct KArgs16 {
     SeqStoreDev Q, T;
+    SeqStoreDev QA;         // even-aligned copy of the stream store (single-block kernels, stream_block16_fa)
     const int16_t* subst;
     int C, go, ge;
     const Item16* items;
@@ -1609,7 +1904,10 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
         const uint8_t* tcB = a.T.codes + b0;
         const uint32_t mmax = mA > mB ? mA : mB;
 
-        const uint64_t x0 = a.Q.off[it.q_begin], x1 = a.Q.off[it.q_end];
+        // single-block templates: moving frame over the even-aligned stream (stream_block16_fa)
+        constexpr bool kFrame = BSA_ALIGNED && !MULTI;
+        const uint64_t* __restrict__ xoff = kFrame ? a.QA.off : a.Q.off;
+        const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
         const uint64_t span = x1 - x0;
         const uint64_t head = span - span * 3 / 16;
         const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
@@ -1645,8 +1943,14 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
                 for (int e = 0; e < 4; ++e) {
                     const int c = 4 * v + e;
                     const uint32_t col = colbase + ln * K + c;
-                    const int sa = (c < K && col < mA) ? (int)s_subst[code * a.C + (vA[col] & kCodeMask)] : 0;
-                    const int sb = (c < K && col < mB) ? (int)s_subst[code * a.C + (vB[col] & kCodeMask)] : 0;
+                    int sa = (c < K && col < mA) ? (int)s_subst[code * a.C + (vA[col] & kCodeMask)] : 0;
+                    int sb = (c < K && col < mB) ? (int)s_subst[code * a.C + (vB[col] & kCodeMask)] : 0;
+                    if (kFrame) {
+                        // frame: the diagonal adds s - 2 ge; the PAD row adds 0 (go - ge in DP column 1)
+                        const int padv = col == 0 ? a.go - a.ge : 0;
+                        if (c < K && col < mA) sa = code == (int)kPadCode ? padv : sa - 2 * a.ge;
+                        if (c < K && col < mB) sb = code == (int)kPadCode ? padv : sb - 2 * a.ge;
+                    }
                     o[e] = ((uint32_t)sa & 0xffffu) | ((uint32_t)sb << 16);
                 }
                 prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1673,7 +1977,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
             const int lastB = hasB ? (int)((mB - 1 - colbase) / K) : -1;
             const int slotB = hasB ? (int)((mB - 1 - colbase) % K) : 0;
             const long long jl = (long long)colbase + (long long)lane * K;
-            const uint32_t hdiag0 = jl == 0 ? kBias2 : pack2b((int)(a.go + (jl - 1) * a.ge));
+            const uint32_t hdiag0 = jl == 0 ? kBias2
+                                            : pack2b(kFrame ? a.go - a.ge : (int)(a.go + (jl - 1) * a.ge));
             for (;;) {
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(&s_chunk, 1u);
@@ -1682,12 +1987,16 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
                 const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
                 const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig
                                                   : head + (span - head) * (c + 1 - nbig) / nsmall;
-                const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + ca);
+                const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + ca);
                 const uint32_t qb = c + 1 == nch ? it.q_end
-                                                 : lower_bound_off(a.Q.off, it.q_begin, it.q_end, x0 + cb);
-                const uint64_t g0 = a.Q.off[qa], g1 = a.Q.off[qb];
+                                                 : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + cb);
+                const uint64_t g0 = xoff[qa], g1 = xoff[qb];
                 if (g1 <= g0) continue;
-                if constexpr (!MULTI)
+                if constexpr (kFrame)
+                    stream_block16_fa<K>(a.QA.codes, g0, g1, prof, lane, lastA, slotA, lastB, slotB, hdiag0,
+                                         pack2b(a.go - a.ge), pack2(a.go - a.ge), a.ge, (int)mA, (int)mB, a.scores,
+                                         it.outA + (qa - it.q_begin), it.outB + (qa - it.q_begin), a.Q.off + qa);
+                else if constexpr (!MULTI)
                     stream_block16_2r<K>(a.Q.codes, g0, g1, prof, rsH, rsF, lane, lastA, slotA, lastB, slotB, hdiag0,
                                          GE, GO, GO32, a.one, a.scores, it.outA + (qa - it.q_begin),
                                          it.outB + (qa - it.q_begin));
@@ -1949,6 +2258,16 @@ __global__ void gather_seqs_kernel(const SeqStoreDev src, const uint32_t* __rest
                                    const uint64_t* __restrict__ dst_off, uint8_t* __restrict__ dst) {
     const uint32_t i = blockIdx.x;
     const uint64_t s0 = src.off[idx[i]], len = src.off[idx[i] + 1] - s0, d0 = dst_off[i];
+    for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) dst[d0 + k] = src.codes[s0 + k];
+}
+
+// Even-aligned copy of a store (bsa_api.cu, build_aligned): sequence i goes to dst_off[i] (even), an
+// odd-length one behind a PAD byte; codes keep their last-residue flags, which end up on odd positions.
+__global__ void align_seqs_kernel(const SeqStoreDev src, const uint64_t* __restrict__ dst_off,
+                                  uint8_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x;
+    const uint64_t s0 = src.off[i], len = src.off[i + 1] - s0, d0 = dst_off[i] + (len & 1u);
+    if ((len & 1u) && threadIdx.x == 0) dst[d0 - 1] = (uint8_t)kPadCode;
     for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) dst[d0 + k] = src.codes[s0 + k];
 }
 

@@ -120,7 +120,7 @@ def tagged_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
     return v >> (cs + xb + 2), v & (U - 1)
 
 
-def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
+def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16, pad=False, phase=0):
     """Model of the FRAME cell (gotoh_kernels.cuh, TAG mode since round 2): the TAG cell in a moving
     frame.  Every stored DP value of cell (i, j) carries score - (i + j) * ge, so that BOTH gap
     extensions cost nothing in the frame:
@@ -131,9 +131,19 @@ def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
       * F needs no addition at all: the OPENING candidate of row i carries x = R-1 - (i mod R), so an
         older opening outranks a newer one on ties; every R rows the stored F values get the top bit of x
         (an OR), which outranks every candidate of the next R rows.
-    6 instructions per cell: IMAD (diagonal), VIMNMX3, LOP3, IMAD (E opening), 2 VIADDMNMX."""
+    6 instructions per cell: IMAD (diagonal), VIMNMX3, LOP3, IMAD (E opening), 2 VIADDMNMX.
+    pad=True models the EVEN-ALIGNED stream of the two-row kernels (stream_block_tag2): a query of odd
+    length is preceded by one PAD row whose profile row adds 0 on the diagonal of the frame (go - ge in
+    DP column 1), which reproduces the top border exactly -- H* = go - ge, the stored F keep their top tag
+    bit -- so the end-of-sequence flag always sits on the second row of a double step; the only special
+    case is the first real row's diagonal input in column 1, H*[0][0] = 0, which lane 0 takes when the
+    row above is the PAD row.  `phase` is where the query starts inside the kernel's blocks of R rows."""
     n, m = len(q), len(t)
     assert R & (R - 1) == 0 and R <= 1 << (xb - 1)
+    PAD = -1
+    rows = list(q)
+    if pad and n % 2 == 1:
+        rows = [PAD] + rows
     U, X1 = 1 << cs, 1 << cs
     P1 = 1 << (cs + xb)
     S = 1 << (cs + xb + 2)
@@ -145,23 +155,26 @@ def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
     HB = (go - ge) * S                      # H*[0][j], j >= 1, and H*[i][0], i >= 1
     gaps = (ord("-"), ord("_"))
 
-    def T(a, b):
+    def T(a, b, c):
+        if a == PAD:
+            return (HB if c == 0 else 0) + 3 * P1
         ident = 1 if (cs > 0 and a == b and a not in gaps) else 0
         return (score[aa[a] * 21 + aa[b]] - 2 * ge) * S + 3 * P1 + ident
 
     Hc = [HB] * m
     Fr = [HB + GOF + XTOP] * m             # eager F of row 1: opened from the top border, older than any candidate
     lo, hi = 0, 0
-    for i in range(n):
-        if i % R == 0:
+    for i in range(len(rows)):
+        g = phase + i
+        if g % R == 0:
             Fr = [f | XTOP for f in Fr]
-        cF = GOF + (R - 1 - i % R) * X1
+        cF = GOF + (R - 1 - g % R) * X1
         er = HB + GOE
-        hd = 0 if i == 0 else HB
+        hd = 0 if (i == 0 or rows[i - 1] == PAD) else HB
         for c in range(m):
             if c % K == 0:
                 er &= ~XMASK                      # lane boundary: after the shuffle
-            d = hd + T(q[i], t[c])
+            d = hd + T(rows[i], t[c], c)
             h = max(d, er, Fr[c])
             hc = h & MASK
             er = max(er + X1, hc + GOE)
@@ -177,6 +190,56 @@ def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
         return go + (m - 1) * ge, 0
     v = Hc[m - 1]
     return (v >> (cs + xb + 2)) + (n + m) * ge, v & (U - 1)
+
+
+def frame16_align(q, t, score, aa, go, ge, pad=True, mpad=0):
+    """Model of the 16-bit score-only cell in the moving frame (gotoh_kernels.cuh, stream_block16_fa): one
+    half of a packed register, biased by 0x8000, every operation modulo 2**16 as the U16x2 instructions do:
+        t = max(hd + T, e)   h = max(t, f)   e = max(h + (go - ge), e)   f = max(h + (go - ge), f)
+    borders go - ge / 2 (go - ge), a PAD row (profile 0; go - ge in DP column 1) ahead of odd-length queries,
+    `mpad` extra padded columns with profile 0 to the right (the shorter template of a pair).
+    Returns the score, or None when a value leaves the 16-bit range (the host's range check must refuse it)."""
+    n, m = len(q), len(t)
+    if m == 0:
+        return 0 if n == 0 else go + (n - 1) * ge
+    if n == 0:
+        return go + (m - 1) * ge
+    B, M16 = 0x8000, 0xffff
+    PAD = -1
+    rows = ([PAD] if pad and n % 2 else []) + list(q)
+    ok = [True]
+
+    def wadd(a, b):                      # 16-bit wrapping add of a two's-complement addend to a biased value
+        r = a + b
+        if not 0 <= r <= M16:
+            ok[0] = False
+        return r & M16
+
+    def T(a, c):
+        if c >= m:
+            return 0
+        if a == PAD:
+            return (go - ge) if c == 0 else 0
+        return score[aa[a] * 21 + aa[t[c]]] - 2 * ge
+
+    HB = B + go - ge
+    GOF = go - ge
+    FB = wadd(HB, GOF)
+    W = m + mpad
+    H = [HB] * W
+    F = [FB] * W
+    for i, a in enumerate(rows):
+        hd = B if (i == 0 or rows[i - 1] == PAD) else HB      # H*[.][0] of the row above; H*[0][0] = 0
+        e = FB
+        for c in range(W):
+            tt = max(wadd(hd, T(a, c)), e)
+            h = max(tt, F[c])
+            e = max(wadd(h, GOF), e)
+            F[c] = max(wadd(h, GOF), F[c])
+            hd, H[c] = H[c], h
+    if not ok[0]:
+        return None
+    return H[m - 1] - B + (n + m) * ge
 
 
 def wave_frame_align(q, t, score, aa, go, ge, pre=4):

@@ -119,6 +119,10 @@ def test_frame_lane_model_matches_oracle(alphabet):
         for K, R, xb in ((4, 16, 5), (1, 1, 1), (20, 16, 5), (3, 4, 3), (7, 2, 5)):
             s, nid = frame_align(q, t, psc, pai, go, ge, cs, xb=xb, K=K, R=R)
             assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R)
+            # the even-aligned stream of the two-row kernels: a PAD row ahead of odd-length queries,
+            # the query starting anywhere inside a block of R rows
+            s, nid = frame_align(q, t, psc, pai, go, ge, cs, xb=xb, K=K, R=R, pad=True, phase=(k * 5 + K) % 32)
+            assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R, "pad")
 
 
 @pytest.mark.parametrize("alphabet", [AA, DIRTY])
@@ -171,3 +175,23 @@ def test_wave_ring_hand_off_schedule_model():
                 covered = sorted((f, l) for _, f, l, _ in fetches)
                 assert covered[0][0] == 0 and covered[-1][1] == X
                 assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+
+
+@pytest.mark.parametrize("alphabet", [AA, DIRTY])
+def test_frame16_cell_model_matches_oracle(alphabet):
+    """The 16-bit score-only cell in the moving frame over the even-aligned stream (4 DPX instructions per two
+    cells, constant borders, a PAD row ahead of odd-length queries, padded columns) gives the reference's score."""
+    from packed_model import frame16_align
+    text = ncbi_text("BLOSUM62")
+    sc, ai = c_oracle.parse_ncbi(text)
+    psc, pai = pyoracle.parse_ncbi(text)
+    k = 0
+    for q, t in pairs(53, 400, 70, alphabet):
+        go, ge = GAPS[k % len(GAPS)]
+        k += 1
+        if ge == 0 and max(len(q), len(t)) < 2:
+            continue
+        ref = c_oracle.align_pair(q, t, sc, ai, go, ge, max(len(q), len(t)) + 100 * (k % 3))
+        for pad, mpad in ((True, 0), (False, 0), (True, 9)):
+            s = frame16_align(q, t, psc, pai, go, ge, pad=pad, mpad=mpad)
+            assert s == ref["score"], (q, t, go, ge, pad, mpad)
