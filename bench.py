@@ -55,16 +55,16 @@ LAW = "UniRef50-like lengths (lognormal mu=5.45 sigma=0.65, 30..4000), 25% homol
 ROOF = {
     # frame cell (TAG kernels, round 2): 4 ALU-pipe + 2 IMAD (gotoh_stream_kernel / gotoh_pair_kernel)
     "tag": dict(ops=6.0, which=8, mix="frame cell: VIMNMX3 + LOP3 + 2 VIADDMNMX + 2 IMAD"),
-    # 16-bit packed score-only cell: 4 ALU-pipe instructions per TWO cells (gotoh_score16_kernel)
-    "s16": dict(ops=2.0, which=6, mix="ALU-pipe instructions of the u16x2 cell against the VIADDMNMX.S16x2 rate"),
+    # 16-bit packed score-only cell in the moving frame: 4 DPX instructions per TWO cells, nothing else (gotoh_score16_kernel)
+    "s16": dict(ops=2.0, which=6, mix="u16x2 frame cell (3 VIADDMNMX.U16x2 + VIMNMX.U16x2 per two cells) against the VIADDMNMX.S16x2 rate"),
     # K3 direction-frame cell (gotoh_wave_kernel, round 2): 8 ALU-pipe (VIMNMX3, 4 LOP3, 2 VIADDMNMX, SHF) + 3 IMAD
     "dirs": dict(ops=11.0, which=9, mix="K3 direction-frame cell: VIMNMX3 + 4 LOP3 + 2 VIADDMNMX + SHF + 3 IMAD"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
 # captures committed under profiles/ (quoted, not re-measured per run: counters need a profiler)
 TRAFFIC_QUOTED = {
-    "tag": dict(bytes=3086080, source="profiles/r2_ncu_summary_k1.md: gotoh_pair_kernel<17,TAG>, 42.6 ms launch of the cfg2 run"),
-    "s16": dict(bytes=None, source=None),
+    "tag": dict(bytes=3194112, source="profiles/r2_ncu_summary_k1_aligned.md: gotoh_stream_kernel<17,single,TAG>, 41.8 ms launch of the cfg2 run"),
+    "s16": dict(bytes=936448, source="profiles/r2_ncu_summary_k1s_frame.md: gotoh_score16_kernel<16,single>, 9.2 ms launch of a 1000 x 20000 run"),
     "dirs": dict(bytes=4381725952, source="profiles/r2_ncu_summary_wave_frame.md: gotoh_wave_kernel on cfg5, 4.20 GB of directions written + 0.18 GB read"),
 }
 

@@ -244,12 +244,29 @@ def test_score_only_16bit_lanes(ctx, oracle_matrices):
     scores must equal the oracle's (and the 32-bit kernel's)."""
     rng = random.Random(41)
     Q = [bytes(rng.choice(AA) for _ in range(rng.randint(1, 400))) for _ in range(90)]
+    # long queries too: against the long templates they stay out of the 16-bit owner swap (long x long)
+    Q += [bytes(rng.choice(AA) for _ in range(n)) for n in (641, 700, 1501)]
     T = [bytes(rng.choice(AA) for _ in range(n)) for n in
          [1, 2, 31, 32, 33, 64, 100, 101, 233, 240, 250, 256, 300, 600, 640, 641, 700, 1290, 1300, 2000, 2100]]
-    T += [Q[3], Q[10][:50], Q[20] + Q[21]]
+    T += [Q[3], Q[10][:50], Q[20] + Q[21], Q[91][:650] + Q[5]]
     M = oracle_matrices["BLOSUM62"]
     qr, qo = bs.pack(Q)
     tr, to = bs.pack(T)
+    # a matrix that is NOT symmetric: the owner swap (long templates streamed as rows through the queries'
+    # columns) must look the substitution score up transposed
+    asym = bs.SubstitutionMatrix(M[0].copy(), M[1])
+    asym.score[0 * 21 + 1] += 2
+    asym.score[5 * 21 + 7] -= 3
+    asym.score[10 * 21 + 9] += 1
+    ctx.set_scoring(asym, -10, -1)
+    ctx.load_sequences(0, qr, qo)
+    ctx.load_sequences(1, tr, to)
+    s16, _ = ctx.one_vs_many(0, 1, want_identical=False)
+    ref = c_oracle.align_all_pairs(c_oracle.SeqSet(Q), c_oracle.SeqSet(T), asym.score, M[1], -10, -1, False,
+                                   n_threads=8, with_backtrace=False)
+    assert np.array_equal(s16, ref["score"]), "asymmetric matrix"
+    s32, _ = ctx.one_vs_many(0, 1, want_identical=True)
+    assert np.array_equal(s16, s32), "asymmetric matrix, 32-bit lanes"
     for go, ge in ((-10, -1), (-11, -2), (-4, -4)):
         ctx.set_scoring("BLOSUM62", go, ge)
         ctx.load_sequences(0, qr, qo)
