@@ -977,7 +977,12 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     ctx->stats.cells = (uint64_t)total_cells;
     if (n_res == 0) return BSA_OK;
 
-    const double target_cells = std::min(std::max(total_cells / 40000.0, 1048576.0), 268435456.0);
+    // item size: ~40,000 items for a large problem; small problems get fewer, larger items (the ~100 kernel groups
+    // run on concurrent streams and need not fill the GPU one by one, and the per-item costs -- profile build,
+    // barriers, pipeline fill of short chunks -- are what such a run is made of)
+    const char* min_item_env = getenv("BSA_MIN_ITEM_CELLS");        // A/B only
+    const double min_item = min_item_env ? atof(min_item_env) : 4194304.0;
+    const double target_cells = std::min(std::max(total_cells / 40000.0, min_item), 268435456.0);
     struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0, swept = 0; };
     const bool use_tag = !getenv("BSA_NO_TAG");
     std::vector<Fix> fixes;

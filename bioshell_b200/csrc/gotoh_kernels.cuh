@@ -1116,6 +1116,32 @@ struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= BSA_MB3_MAXK 
 constexpr uint32_t kChunkBig = BSA_CHUNK_BIG;    // stream residues per chunk (pipeline fill is 31 steps)
 constexpr uint32_t kChunkSmall = 640;
 
+// Chunk schedule of one item's stream: big chunks over the first 13/16, small ones over the rest, so the warps
+// reach the item's closing barrier within half a small chunk of each other.  The big chunks shrink with the
+// stream so that every warp gets at least two of them, and a short stream (small problems: items of a few
+// thousand residues) is cut into uniform pieces -- with fixed 4,096-residue chunks one warp swept most of such
+// an item while the other seven waited at the barrier.
+struct ChunkPlan { uint64_t head; uint32_t nbig, nsmall; };
+__device__ __forceinline__ ChunkPlan plan_chunks(uint64_t span) {
+    constexpr uint64_t W = kWarpsPerCta;
+    ChunkPlan p;
+    if (span < 4u * W * kChunkSmall) {
+        uint64_t lb = span / (2 * W);
+        if (lb < 192) lb = 192;
+        p.head = span;
+        p.nbig = (uint32_t)((span + lb - 1) / lb);
+        p.nsmall = 0;
+    } else {
+        p.head = span - span * 3 / 16;
+        uint64_t lb = p.head / (2 * W);
+        lb = lb < kChunkSmall ? kChunkSmall : (lb > kChunkBig ? kChunkBig : lb);
+        p.nbig = (uint32_t)((p.head + lb - 1) / lb);
+        p.nsmall = (uint32_t)((span - p.head + kChunkSmall - 1) / kChunkSmall);
+        if (p.nsmall < (uint32_t)W) p.nsmall = (uint32_t)W;
+    }
+    return p;
+}
+
 template <int K, bool MULTI, bool TAG = false>
 __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_kernel(const KArgs a) {
     extern __shared__ uint4 smem[];
@@ -1146,10 +1172,9 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
         const uint64_t* __restrict__ xoff = kAligned ? a.QA.off : a.Q.off;
         const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
         const uint64_t span = x1 - x0;
-        const uint64_t head = span - span * 3 / 16;
-        const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
-        uint32_t nsmall = (uint32_t)((span - head + kChunkSmall - 1) / kChunkSmall);
-        if (nsmall < (uint32_t)kWarpsPerCta) nsmall = kWarpsPerCta;
+        const ChunkPlan cp = plan_chunks(span);
+        const uint64_t head = cp.head;
+        const uint32_t nbig = cp.nbig, nsmall = cp.nsmall;
         const uint32_t nch = nbig + nsmall;
         const uint32_t npass = MULTI ? (m + 32 * K - 1) / (32 * K) : 1u;
         // MULTI: the boundary column of the whole item, addressed by stream position
@@ -1764,10 +1789,9 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const uint64_t* __restrict__ xoff = kAligned ? a.QA.off : a.Q.off;
         const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
         const uint64_t span = x1 - x0;
-        const uint64_t head = span - span * 3 / 16;
-        const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
-        uint32_t nsmall = (uint32_t)((span - head + kChunkSmall - 1) / kChunkSmall);
-        if (nsmall < (uint32_t)kWarpsPerCta) nsmall = kWarpsPerCta;
+        const ChunkPlan cp = plan_chunks(span);
+        const uint64_t head = cp.head;
+        const uint32_t nbig = cp.nbig, nsmall = cp.nsmall;
         const uint32_t nch = nbig + nsmall;
 
         __syncthreads();
@@ -1909,10 +1933,9 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
         const uint64_t* __restrict__ xoff = kFrame ? a.QA.off : a.Q.off;
         const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
         const uint64_t span = x1 - x0;
-        const uint64_t head = span - span * 3 / 16;
-        const uint32_t nbig = (uint32_t)((head + kChunkBig - 1) / kChunkBig);
-        uint32_t nsmall = (uint32_t)((span - head + kChunkSmall - 1) / kChunkSmall);
-        if (nsmall < (uint32_t)kWarpsPerCta) nsmall = kWarpsPerCta;
+        const ChunkPlan cp = plan_chunks(span);
+        const uint64_t head = cp.head;
+        const uint32_t nbig = cp.nbig, nsmall = cp.nsmall;
         const uint32_t nch = nbig + nsmall;
         const uint32_t npass = MULTI ? (mmax + 32 * K - 1) / (32 * K) : 1u;
         uint2* scratch = MULTI ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : nullptr;
