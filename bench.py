@@ -53,12 +53,16 @@ LAW = "UniRef50-like lengths (lognormal mu=5.45 sigma=0.65, 30..4000), 25% homol
 
 # lane-instructions per cell of the dominant kernel and the bsa_measure_int_peak mix they are held against
 ROOF = {
-    # frame cell (TAG kernels, round 2): 4 ALU-pipe + 2 IMAD (gotoh_stream_kernel / gotoh_pair_kernel)
-    "tag": dict(ops=6.0, which=8, mix="frame cell: VIMNMX3 + LOP3 + 2 VIADDMNMX + 2 IMAD"),
+    # frame cell with column-tagged E openings (TAG kernels, round 2): 4 ALU-pipe + 1 IMAD (gotoh_stream_kernel /
+    # gotoh_pair_kernel; the multi-pass groups, 3 % of cfg2's cells, still run the 6-instruction form)
+    "tag": dict(ops=5.0, which=10, mix="frame cell, E openings tagged by column: VIMNMX3 + LOP3 + 2 VIADDMNMX + IMAD",
+                alu_ops=4.0),
     # 16-bit packed score-only cell in the moving frame: 4 DPX instructions per TWO cells, nothing else (gotoh_score16_kernel)
-    "s16": dict(ops=2.0, which=6, mix="u16x2 frame cell (3 VIADDMNMX.U16x2 + VIMNMX.U16x2 per two cells) against the VIADDMNMX.S16x2 rate"),
+    "s16": dict(ops=2.0, which=6, mix="u16x2 frame cell (3 VIADDMNMX.U16x2 + VIMNMX.U16x2 per two cells) against the VIADDMNMX.S16x2 rate",
+                alu_ops=2.0),
     # K3 direction-frame cell (gotoh_wave_kernel, round 2): 8 ALU-pipe (VIMNMX3, 4 LOP3, 2 VIADDMNMX, SHF) + 3 IMAD
-    "dirs": dict(ops=11.0, which=9, mix="K3 direction-frame cell: VIMNMX3 + 4 LOP3 + 2 VIADDMNMX + SHF + 3 IMAD"),
+    "dirs": dict(ops=11.0, which=9, mix="K3 direction-frame cell: VIMNMX3 + 4 LOP3 + 2 VIADDMNMX + SHF + 3 IMAD",
+                 alu_ops=8.0),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
 # captures committed under profiles/ (quoted, not re-measured per run: counters need a profiler)
@@ -435,6 +439,7 @@ def main():
 
     roof = ROOF[w.roof]
     peak_ops, peak_mhz = ctx.measure_int_peak(roof["which"])
+    alu_rate, _ = ctx.measure_int_peak(1)      # VIADDMNMX alone: the rate of the ALU pipe that carries the DPX instructions
 
     # whole-job aggregates: max time over ranks, sum of units over ranks
     tv = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -474,6 +479,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
                          "frac": achieved / peak_ops,
+                         # the second, mix-independent denominator: the ALU-pipe instructions of the cell alone against the
+                         # measured rate of that pipe (a bound no instruction mix can beat)
+                         "alu_pipe": {"achieved": per_gpu_cells_s * roof["alu_ops"] / 1e12, "peak": alu_rate / 1e12,
+                                      "unit": "Tlane-op/s", "frac": per_gpu_cells_s * roof["alu_ops"] / alu_rate,
+                                      "ops_per_cell": roof["alu_ops"]},
                          "traffic": tq["bytes"], "traffic_source": tq["source"],
                          "note": "integer/DPX issue roofline per GPU: cells/s x %.1f lane-instructions per cell (%s) in independent "
                                  "chains, measured live by bsa_measure_int_peak (of measured; SM clock %.0f MHz during that probe). "

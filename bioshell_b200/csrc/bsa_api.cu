@@ -1213,7 +1213,11 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         // TAG cells live in the moving frame score - (i + j) ge: [-(4 |go| + ...), max(M) min(n, m) + (n + m) |ge|]
         const int64_t ubf = ub + (int64_t)(V.xmax + m_pad + 10) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
         const int64_t lbf = 4 * (int64_t)(-ctx->go) + 8 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
-        const bool fits_tag = use_tag && std::max(ubf, lbf) + 8 < lim_tag;   // room for the tag field too
+        // single-block TAG kernels size the count field for their columns-per-lane class (a launch constant:
+        // gotoh_stream_kernel, kUniformCs), which can be one bit more than this template needs
+        const int cs_k = (BSA_ALIGNED && BSA_ETAG && !kc.multi) ? std::min(bitlen(32ull * kc.K), V.cs_cap) : cs;
+        const int64_t lim_tag_k = cs_k + kTagBits <= 27 ? (int64_t)1 << (29 - cs_k - kTagBits) : 0;
+        const bool fits_tag = use_tag && std::max(ubf, lbf) + 8 < std::min(lim_tag, lim_tag_k);   // room for the tag field too
         // short owners: keep items small enough that their group still fills the GPU;
         // multi-pass: this also bounds the per-CTA boundary slice (2 MiB)
         uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
@@ -1475,7 +1479,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 const Group& G = V.groups[L.g];
                 KArgs a;
                 memset(&a, 0, sizeof(a));
-                a.Q = V.qdev; a.T = V.tdev; a.QA = V.qadev;
+                a.Q = V.qdev; a.T = V.tdev; a.QA = V.qadev; a.cs_cap = V.cs_cap;
                 a.subst = ctx->d_subst.as<int16_t>(); a.isgap = ctx->d_isgap.as<uint8_t>();
                 a.C = C; a.go = ctx->go; a.ge = ctx->ge; a.one = 1; a.one2 = 1;
                 a.items = ctx->items.as<Item>() + L.item_off;

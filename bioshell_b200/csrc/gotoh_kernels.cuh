@@ -93,6 +93,10 @@
 #define BSA_ALIGNED 1       // two-row blocks read the EVEN-ALIGNED copy of the stream store (a PAD row ahead of odd-length
                             // sequences): end-of-sequence flags only on the second row of a double step, one code path
 #endif
+#ifndef BSA_ETAG
+#define BSA_ETAG 1          // aligned two-row blocks: E openings tagged by column (no addition in the E extension), the
+                            // count-field width a launch constant so that every cell constant is warp-uniform
+#endif
 #ifndef BSA_TWO_ROWS
 #define BSA_TWO_ROWS 1      // two-row step where TwoRows<K, HALF> says so
 #endif
@@ -139,6 +143,7 @@ struct SeqStoreDev {
 struct KArgs {
     SeqStoreDev Q, T;
     SeqStoreDev QA;         // even-aligned copy of the stream store Q (two-row TAG blocks; see stream_block_tag2a)
+    int cs_cap;             // bitlen(longest stream sequence): cap of the count-field width (aligned two-row blocks)
     const int16_t* subst;   // C x C substitution scores by residue code
     const uint8_t* isgap;   // C flags: code is '-' or '_' (never identical, msa.rs:264)
     int C;
@@ -972,8 +977,17 @@ __device__ __forceinline__ void stream_block_tag2a(const uint8_t* __restrict__ c
     // clears the streak field of the E that crossed the lane boundary)
     const int nl0 = opaque_reg(lane0 ? 0 : one);
     const int hbl = opaque_reg(lane0 ? cs.hb0 : 0);
+#if BSA_ETAG
+    // E openings carry the tag K-1-c of their column, so an older opening outranks a newer one on ties and the
+    // extension needs no addition at all: E = max(H + GOE_c, E) is ONE VIADDMNMX with a warp-uniform constant.
+    // An E that crosses a lane boundary gets the full tag field (older than every opening of the next lane).
+    const int xall = ~cs.XCLR;
+    const int ebl = opaque_reg(lane0 ? (cs.hb0 + cs.GOE) | xall : xall);
+    const int keepx = opaque_reg(lane0 ? 0 : -1);
+#else
     const int ebl = opaque_reg(lane0 ? cs.hb0 + cs.GOE : 0);
     const int keepx = opaque_reg(lane0 ? 0 : cs.XCLR);
+#endif
     const int one_a = opaque_reg(one), one_b = opaque_reg(one2);
 
     int H[K], Fr[K], T0[K], T1[K];
@@ -1024,13 +1038,21 @@ __device__ __forceinline__ void stream_block_tag2a(const uint8_t* __restrict__ c
                 const int d0 = hd0 * one_a + T0[c];
                 const int h0 = max3_s32(d0, er0, Fr[c]);
                 const int hc0 = h0 & cs.MASK;
+#if BSA_ETAG
+                er0 = addmax_s32(hc0, cs.GOE + (K - 1 - c) * cs.X1, er0);
+#else
                 er0 = addmax_s32(er0, cs.X1, hc0 * one_a + cs.GOE);
+#endif
                 const int f1 = addmax_s32(hc0, cf0, Fr[c]);
                 hd0 = H[c];
                 const int d1 = hd1 * one_b + T1[c];
                 const int h1 = max3_s32(d1, er1, f1);
                 hc1 = h1 & cs.MASK;
+#if BSA_ETAG
+                er1 = addmax_s32(hc1, cs.GOE + (K - 1 - c) * cs.X1, er1);
+#else
                 er1 = addmax_s32(er1, cs.X1, hc1 * one_b + cs.GOE);
+#endif
                 Fr[c] = addmax_s32(hc1, cf1, f1);
                 hd1 = hc0;
                 H[c] = hc1;
@@ -1163,7 +1185,11 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_stream_ke
         const uint64_t t0 = a.T.off[it.t];
         const uint32_t m = (uint32_t)(a.T.off[it.t + 1] - t0);
         const uint8_t* tc = a.T.codes + t0;
-        const Consts cs = make_consts<K>(a.go, a.ge, (int)it.cshift, false, TAG, a.flip != 0);
+        // aligned two-row blocks: the count field is as wide as the columns-per-lane class needs (a launch constant,
+        // so every constant of the cell is warp-uniform); the host's range check uses the same width
+        constexpr bool kUniformCs = BSA_ALIGNED && BSA_ETAG && TAG && !MULTI && TwoRows<K, false>::value;
+        const int cs_class = (32 - __clz(32 * K)) < a.cs_cap ? (32 - __clz(32 * K)) : a.cs_cap;
+        const Consts cs = make_consts<K>(a.go, a.ge, kUniformCs ? cs_class : (int)it.cshift, false, TAG, a.flip != 0);
 
         // chunk schedule: big chunks over the first 13/16 of the stream, small ones over the rest,
         // so the warps reach the item's closing barrier within half a small chunk of each other
@@ -1781,6 +1807,7 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
         const uint32_t mB = hasB ? (uint32_t)(a.T.off[it.tB + 1] - b0) : 0u;
         const uint32_t mmax = mA > mB ? mA : mB;
         int cshift = 32 - __clz((int)mmax);
+        if (BSA_ALIGNED && BSA_ETAG && TAG && TwoRows<K, true>::value) cshift = 32 - __clz(16 * K);   // launch constant
         cshift = cshift < a.cs_cap ? cshift : a.cs_cap;
         const Consts cs = make_consts<K>(a.go, a.ge, cshift, false, TAG, a.flip != 0);
         const int S = 1 << cs.sh, P3 = 3 << cs.ps;

@@ -61,6 +61,14 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int seed, int one, int on
                 a[i] = __viaddmax_s32(a[i], ge, hc * one2 + go);
                 b[i] = __viaddmax_s32(hc, ph, b[i]);
                 c[i] = hc;
+            } else if (WHICH == 10) {
+                // the FRAME cell with column-tagged E openings (BSA_ETAG): VIMNMX3 + LOP3 + 2 VIADDMNMX (ALU pipe) + 1 IMAD
+                const int d = c[i] * one + ge;
+                const int h = __vimax3_s32(d, a[i], b[i]);
+                const int hc = h & mask;
+                a[i] = __viaddmax_s32(hc, go, a[i]);
+                b[i] = __viaddmax_s32(hc, ph, b[i]);
+                c[i] = hc;
             } else if (WHICH == 9) {
                 // the K3 direction-frame cell (wave_kernels.cuh): VIMNMX3 + 4 LOP3 + 2 VIADDMNMX + SHF (ALU pipe) + 3 IMAD
                 const int d = c[i] * one + ge;
@@ -109,6 +117,7 @@ inline int peak_ops_per_iter(int which) {
         case 7: return 7;
         case 8: return 6;
         case 9: return 11;
+        case 10: return 5;
         case 2: return 2;   // VIMNMX3 + the LOP3 that perturbs it
         default: return 1;
     }
@@ -137,6 +146,7 @@ inline cudaError_t measure_int_peak(int which, int sms, cudaStream_t st, double*
             case 7: int_peak_kernel<7><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             case 8: int_peak_kernel<8><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             case 9: int_peak_kernel<9><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
+            case 10: int_peak_kernel<10><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
             default: int_peak_kernel<6><<<blocks, 256, 0, st>>>(1, 1, 1, sink, clk); break;
         }
     };

@@ -227,7 +227,10 @@ int bsa_get_stats(const bsa_ctx *ctx, bsa_stats *out);
  * measured denominator of the integer/DPX roofline.
  * which: 0 = the 8-op classic cell mix, 1 = VIADDMNMX only, 2 = VIMNMX3 only, 3 = LOP3 only,
  *        4 = IADD3 only, 5 = IMAD only, 6 = VIADDMNMX.S16x2 only,
- *        7 = the 7-op TAG cell mix (VIMNMX3 + LOP3 + 2 VIADDMNMX + 3 IMAD; what bench.py uses)
+ *        7 = the 7-op TAG cell mix of round 1 (VIMNMX3 + LOP3 + 2 VIADDMNMX + 3 IMAD),
+ *        8 = the 6-op frame cell (2 IMAD), 9 = the 11-op K3 direction-frame cell,
+ *        10 = the 5-op frame cell with column-tagged E openings (VIMNMX3 + LOP3 + 2 VIADDMNMX + 1 IMAD;
+ *             what bench.py holds cfg1..cfg3 against)
  */
 int bsa_measure_int_peak(bsa_ctx *ctx, int which, double *lane_ops_per_s, double *sm_clock_mhz);
 

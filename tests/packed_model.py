@@ -120,7 +120,7 @@ def tagged_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16):
     return v >> (cs + xb + 2), v & (U - 1)
 
 
-def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16, pad=False, phase=0):
+def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16, pad=False, phase=0, etag=False):
     """Model of the FRAME cell (gotoh_kernels.cuh, TAG mode since round 2): the TAG cell in a moving
     frame.  Every stored DP value of cell (i, j) carries score - (i + j) * ge, so that BOTH gap
     extensions cost nothing in the frame:
@@ -137,7 +137,11 @@ def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16, pad=False, phase=0
     DP column 1), which reproduces the top border exactly -- H* = go - ge, the stored F keep their top tag
     bit -- so the end-of-sequence flag always sits on the second row of a double step; the only special
     case is the first real row's diagonal input in column 1, H*[0][0] = 0, which lane 0 takes when the
-    row above is the PAD row.  `phase` is where the query starts inside the kernel's blocks of R rows."""
+    row above is the PAD row.  `phase` is where the query starts inside the kernel's blocks of R rows.
+    etag=True models BSA_ETAG: E uses the scheme of F along the columns of a lane -- the OPENING of column c
+    carries the tag K-1-c, the extension adds nothing (E = max(H + GOE_c, E), one VIADDMNMX with a warp-uniform
+    constant), and an E that crosses a lane boundary gets the full tag field, older than every opening of the
+    next lane: 5 instructions per cell (IMAD, VIMNMX3, LOP3, 2 VIADDMNMX)."""
     n, m = len(q), len(t)
     assert R & (R - 1) == 0 and R <= 1 << (xb - 1)
     PAD = -1
@@ -173,13 +177,17 @@ def frame_align(q, t, score, aa, go, ge, cs, xb=5, K=4, R=16, pad=False, phase=0
         hd = 0 if (i == 0 or rows[i - 1] == PAD) else HB
         for c in range(m):
             if c % K == 0:
-                er &= ~XMASK                      # lane boundary: after the shuffle
+                er = (er | XMASK) if etag else (er & ~XMASK)      # lane boundary: after the shuffle
             d = hd + T(rows[i], t[c], c)
             h = max(d, er, Fr[c])
             hc = h & MASK
-            er = max(er + X1, hc + GOE)
+            if etag:
+                assert K - 1 < (1 << xb) - 1
+                er = max(hc + GOE + (K - 1 - c % K) * X1, er)
+            else:
+                er = max(er + X1, hc + GOE)
             Fr[c] = max(hc + cF, Fr[c])
-            assert (er & XMASK) >> cs <= K
+            assert etag or (er & XMASK) >> cs <= K
             assert (er >> (cs + xb)) & 3 == 2 and (Fr[c] >> (cs + xb)) & 3 == 1
             lo, hi = min(lo, d, er, Fr[c]), max(hi, d, er, Fr[c])
             hd, Hc[c] = Hc[c], hc

@@ -123,6 +123,12 @@ def test_frame_lane_model_matches_oracle(alphabet):
             # the query starting anywhere inside a block of R rows
             s, nid = frame_align(q, t, psc, pai, go, ge, cs, xb=xb, K=K, R=R, pad=True, phase=(k * 5 + K) % 32)
             assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R, "pad")
+            # ... with the E openings tagged by column instead of the streak count (BSA_ETAG), and the count field
+            # as wide as the columns-per-lane class needs instead of the template
+            for cs2 in (cs, cs + 1):
+                s, nid = frame_align(q, t, psc, pai, go, ge, cs2, xb=max(xb, 2), K=K, R=R, pad=True,
+                                     phase=(k * 3 + K) % 32, etag=True)
+                assert (s, nid) == (ref["score"], ref["n_identical"]), (q, t, go, ge, K, R, "etag")
 
 
 @pytest.mark.parametrize("alphabet", [AA, DIRTY])
