@@ -46,6 +46,9 @@
 #ifndef BSA_TAG2_U
 #define BSA_TAG2_U 4        // double steps per loop iteration of the two-row blocks (same-box A/B on cfg2: 2 -> 3195, 4 -> 3284, 8 -> 3024, 1 -> 3026 GCUPS)
 #endif
+#ifndef BSA_TAG2_U_SMALLK
+#define BSA_TAG2_U_SMALLK 0  // aligned two-row blocks with at most this many columns per lane take 8 double steps per iteration (measured with 6 and 10: no gain on cfg2 / one-vs-many, -4..-8 % on 1,000 sequences: off)
+#endif
 #ifndef BSA_RING
 #define BSA_RING 0          // warp-wide prefetch (measured -0.4 % on cfg2: off) of the boundary column in multi-pass kernels
 #endif
@@ -965,7 +968,7 @@ __device__ __forceinline__ void stream_block_tag2a(const uint8_t* __restrict__ c
                                                    const uint64_t* __restrict__ lutp,
                                                    const uint64_t* __restrict__ qoffp) {
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
-    constexpr int U = BSA_TAG2_U;  // double steps per loop iteration
+    constexpr int U = K <= BSA_TAG2_U_SMALLK ? 8 : BSA_TAG2_U;  // double steps per loop iteration
     static_assert(8 % U == 0, "the stored F get the top tag bit every 8 double steps");
     const uint32_t X = (uint32_t)(g1 - g0);        // even
     const int span = HALF ? 15 : lane_last;
@@ -1689,7 +1692,7 @@ __device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ co
                                                   int32_t* __restrict__ scores, uint64_t outA, uint64_t outB,
                                                   const uint64_t* __restrict__ qoffp) {
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
-    constexpr int U = BSA_TAG2_U;
+    constexpr int U = K <= BSA_TAG2_U_SMALLK ? 8 : BSA_TAG2_U;
     const uint32_t X = (uint32_t)(g1 - g0);        // even
     const int span = lastA > lastB ? lastA : lastB;
     const uint32_t nd = (X / 2u + (uint32_t)span + (U - 1)) / U * U;
