@@ -239,6 +239,29 @@ def test_unsupported_gap_settings_are_refused(ctx):
         ctx.load_sequences(0, np.array([65, 255, 66], np.uint8), np.array([0, 3], np.uint64))
 
 
+def test_alphabet_limit_and_odd_even_lengths(oracle_matrices):
+    """Residue code 0 is reserved for the PAD rows of the even-aligned stream: 127 distinct byte values
+    are accepted (and align like the oracle, unknown bytes scoring as 'A'), the 128th is refused.
+    Lengths of both parities side by side: the aligned copy pads only the odd ones."""
+    M = oracle_matrices["BLOSUM62"]
+    rng = random.Random(77)
+    vals = [b for b in range(1, 200) if b not in (ord("-"), ord("_"))][:127]
+    seqs = [bytes(vals[i:i + n]) for i, n in ((0, 40), (40, 41), (81, 46), (3, 1), (90, 2), (60, 67))]
+    seqs += [bytes(rng.choice(AA) for _ in range(n)) for n in (1, 2, 3, 4, 5, 63, 64, 65, 127, 128, 129, 300, 301)]
+    res, off = bs.pack(seqs)
+    with bs.Context(0) as c:
+        c.set_scoring("BLOSUM62", -10, -1)
+        c.load_sequences(0, res, off)
+        scores, nid = c.all_vs_all(0)
+        ref = oracle_triangle(res, off, M, -10, -1)
+        assert np.array_equal(scores, ref["score"]) and np.array_equal(nid, ref["n_identical"])
+        s16, _ = c.all_vs_all(0, want_identical=False)
+        assert np.array_equal(s16, ref["score"])
+        with pytest.raises(bs.BsaError) as e:
+            c.load_sequences(1, np.array([vals[0], 250], np.uint8), np.array([0, 2], np.uint64))
+        assert e.value.rc == -7
+
+
 def test_score_only_16bit_lanes(ctx, oracle_matrices):
     """Score-only requests pair two templates per warp in s16x2 lanes (gotoh_score16_kernel);
     scores must equal the oracle's (and the 32-bit kernel's)."""
