@@ -62,7 +62,7 @@ extern "C" {
 #define BSA_ERR_CUDA (-4)
 #define BSA_ERR_OOM (-5)
 #define BSA_ERR_FORMAT (-6)           /* NCBI matrix text: IncorrectNCBIFormat / CantParseNCBIEntry */
-#define BSA_ERR_ALPHABET (-7)         /* > 128 distinct residue byte values, or byte 255 (reference panics) */
+#define BSA_ERR_ALPHABET (-7)         /* > 127 distinct residue byte values, or byte 255 (reference panics) */
 #define BSA_ERR_EMPTY (-8)            /* empty sequence set (reference: max().unwrap() panics) */
 
 /* flags for the alignment entry points */
