@@ -197,6 +197,7 @@ __device__ __forceinline__ int wave_block_frame(const uint8_t* __restrict__ qc, 
 
     for (uint32_t S0 = 0; S0 < nd; S0 += 4u) {
         // ---- every 4 steps: refill the rings ----
+        __syncwarp();   // the ring entries rewritten below were last read (by every lane, fetching ahead) in the steps before
         if ((S0 & 15u) == 0u) {
             const int t = 4 * (int)(S0 + 16u) + 2 * lane;               // steps [S0 + 16, S0 + 32): asked for now,
             rf0 = fetch(t);

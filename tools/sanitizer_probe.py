@@ -16,6 +16,8 @@ with bs.Context(0) as ctx:
     ctx.load_sequences(0, res, off)
     s, n = ctx.all_vs_all(0)
     print("all_vs_all", len(s), int(s.astype(np.int64).sum()), int(n.astype(np.int64).sum()))
+    s16, _ = ctx.one_vs_many(0, 0, want_identical=False)               # 16-bit frame kernels over the aligned stream
+    print("one_vs_many score only", len(s16), int(s16.astype(np.int64).sum()))
     res2, off2 = synth.generate(3, seed=4, dist=0, lo=4200, hi=4600)   # wavefront kernel
     ctx.load_sequences(1, res2, off2)
     s2, n2, p2 = ctx.align_pairs_paths(1, 1, [0, 1], [1, 2])
