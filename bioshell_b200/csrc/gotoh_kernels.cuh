@@ -100,6 +100,9 @@
 #define BSA_ETAG 1          // aligned two-row blocks: E openings tagged by column (no addition in the E extension), the
                             // count-field width a launch constant so that every cell constant is warp-uniform
 #endif
+#ifndef BSA_PADSLOT
+#define BSA_PADSLOT 1       // aligned two-row blocks, K % 4 != 0: lane 0's left-border value rides in the spare slot of the profile row
+#endif
 #ifndef BSA_TWO_ROWS
 #define BSA_TWO_ROWS 1      // two-row step where TwoRows<K, HALF> says so
 #endif
@@ -347,6 +350,9 @@ __device__ __forceinline__ void build_profile(uint4* prof, uint4* rsH, uint4* rs
             const int c = 4 * v + e;
             const uint32_t col = colbase + lane * K + c;
             int val = cs.T_PAD;
+            // spare slot behind the K columns (load_vec_x): lane 0's left-border H* of a row with this residue
+            if (BSA_PADSLOT && K % 4 != 0 && c == K && cs.XTOP && colbase == 0)
+                val = lane == 0 ? (code == (int)kPadCode ? 0 : cs.hb0) : 0;
             if (c < K && col < m) {
                 const int tcode = tc[col] & kCodeMask;
                 val = ((int)subst[a.flip ? tcode * C + code : code * C + tcode] + cs.TSUB) * S + P3 +
@@ -389,6 +395,25 @@ __device__ __forceinline__ void load_vec(int (&dst)[K], const uint4* __restrict_
         if (4 * v + 1 < K) dst[4 * v + 1] = (int)x.y;
         if (4 * v + 2 < K) dst[4 * v + 2] = (int)x.z;
         if (4 * v + 3 < K) dst[4 * v + 3] = (int)x.w;
+    }
+}
+
+// The same row plus the entry behind its K columns (K % 4 != 0: the last vector has a spare slot).  The
+// aligned two-row blocks keep lane 0's left-border value of the row there -- go - ge, or H*[0][0] = 0 in the
+// PAD row, 0 in every other lane -- so the PAD test costs no instruction (BSA_PADSLOT).
+template <int K>
+__device__ __forceinline__ void load_vec_x(int (&dst)[K], int& extra, const uint4* __restrict__ src) {
+    constexpr int V = KTraits<K>::V;
+    static_assert(K % 4 != 0, "no spare slot");
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const uint4 x = src[v * 32];
+        const int w[4] = {(int)x.x, (int)x.y, (int)x.z, (int)x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (4 * v + e < K) dst[4 * v + e] = w[e];
+            if (4 * v + e == K) extra = w[e];
+        }
     }
 }
 
@@ -1019,15 +1044,21 @@ __device__ __forceinline__ void stream_block_tag2a(const uint8_t* __restrict__ c
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t b0 = b[2 * u], b1 = b[2 * u + 1];     // b0 never carries a flag
-            load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+            int hq = 0;
+            if constexpr (BSA_PADSLOT && K % 4 != 0)
+                load_vec_x<K>(T0, hq, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+            else {
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+                hq = b0 == kPadCode ? 0 : hbl;
+            }
             load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b1 & kCodeMask) * ROWB));
             const int sh0 = __shfl_up_sync(0xffffffffu, oh0, 1);
             const int se0 = __shfl_up_sync(0xffffffffu, oe0, 1);
             const int sh1 = __shfl_up_sync(0xffffffffu, oh1, 1);
             const int se1 = __shfl_up_sync(0xffffffffu, oe1, 1);
             // row 1's diagonal input in this lane's first column = row 0's H to the left; for lane 0 the
-            // border, or H*[0][0] = 0 when row 0 is the PAD row
-            const int hin0 = sh0 * nl0 + (b0 == kPadCode ? 0 : hbl);
+            // border, or H*[0][0] = 0 when row 0 is the PAD row (hq: from the profile row's spare slot)
+            const int hin0 = sh0 * nl0 + hq;
             const int hin1 = sh1 * nl0 + hbl;
             int er0 = (se0 & keepx) | ebl;
             int er1 = (se1 & keepx) | ebl;
@@ -1723,13 +1754,19 @@ __device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ co
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t b0 = b[2 * u], b1 = b[2 * u + 1];     // b0 never carries a flag
-            load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+            int hq = 0;
+            if constexpr (BSA_PADSLOT && K % 4 != 0)
+                load_vec_x<K>(T0, hq, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+            else {
+                load_vec<K>(T0, reinterpret_cast<const uint4*>(prof_lane + b0 * ROWB));
+                hq = (int)(b0 == kPadCode ? zbl : hbl);
+            }
             load_vec<K>(T1, reinterpret_cast<const uint4*>(prof_lane + (b1 & kCodeMask) * ROWB));
             const uint32_t sh0 = __shfl_up_sync(0xffffffffu, oh0, 1);
             const uint32_t se0 = __shfl_up_sync(0xffffffffu, oe0, 1);
             const uint32_t sh1 = __shfl_up_sync(0xffffffffu, oh1, 1);
             const uint32_t se1 = __shfl_up_sync(0xffffffffu, oe1, 1);
-            const uint32_t hin0 = (sh0 & keep) | (b0 == kPadCode ? zbl : hbl);
+            const uint32_t hin0 = (sh0 & keep) | (uint32_t)hq;      // hq: lane 0's border of row 0 (0 for the PAD row)
             const uint32_t hin1 = (sh1 & keep) | hbl;
             uint32_t e0 = (se0 & keep) | ebl;
             uint32_t e1 = (se1 & keep) | ebl;
@@ -1850,6 +1887,8 @@ __global__ void __launch_bounds__(kThreads, MinBlocks<K>::value) gotoh_pair_kern
                 const int c = 4 * v + e;
                 const uint32_t col = (uint32_t)(ln & 15) * K + c;
                 int val = cs.T_PAD;
+                if (BSA_PADSLOT && TAG && K % 4 != 0 && c == K)      // spare slot: the left-border H* of lanes 0 and 16
+                    val = (ln & 15) == 0 ? (code == (int)kPadCode ? 0 : cs.hb0) : 0;
                 if (c < K && col < m) {
                     const int tcode = tc[col] & kCodeMask;
                     val = ((int)s_subst[a.flip ? tcode * a.C + code : code * a.C + tcode] + cs.TSUB) * S + P3 +
@@ -2005,6 +2044,9 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
                         if (c < K && col < mB) sb = code == (int)kPadCode ? padv : sb - 2 * a.ge;
                     }
                     o[e] = ((uint32_t)sa & 0xffffu) | ((uint32_t)sb << 16);
+                    // spare slot behind the K columns: lane 0's left-border H* of a row with this residue (both halves)
+                    if (BSA_PADSLOT && kFrame && K % 4 != 0 && c == K)
+                        o[e] = ln == 0 ? (code == (int)kPadCode ? kBias2 : pack2b(a.go - a.ge)) : 0u;
                 }
                 prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
             }
