@@ -1384,9 +1384,27 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     // ---------------- outputs ----------------
     int32_t* d_scores = nullptr;
     uint32_t* d_nid = nullptr;
+    // Page-locked result buffers (bsa_host_alloc_pinned, or any cudaHostAlloc / pinned memory): the kernels store
+    // every result straight into the caller's buffers over the host link -- 8 bytes per pair, fire-and-forget
+    // stores -- so there is no staging copy in HBM and no device-to-host copy at the end of the call
+    // (BSA_MAPPED_OUT=0 keeps the staged copy: A/B).  Pageable buffers are staged and copied as before.
+    bool mapped_out = false;
+    const char* mo_env = getenv("BSA_MAPPED_OUT");
+    if (!out_dev && !(mo_env && mo_env[0] == '0')) {
+        auto dev_alias = [](void* p) -> void* {
+            if (!p) return nullptr;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+        };
+        void* ds = want_s ? dev_alias(scores) : nullptr;
+        void* dn = want_i ? dev_alias(n_identical) : nullptr;
+        if ((!want_s || ds) && (!want_i || dn)) { mapped_out = true; d_scores = (int32_t*)ds; d_nid = (uint32_t*)dn; }
+    }
     if (out_dev) {
         d_scores = want_s ? scores : nullptr;
         d_nid = want_i ? n_identical : nullptr;
+    } else if (mapped_out) {
     } else {
         if (want_s) { CK(ctx->out_scores.ensure(n_res * 4)); d_scores = ctx->out_scores.as<int32_t>(); }
         if (want_i) { CK(ctx->out_nid.ensure(n_res * 4)); d_nid = ctx->out_nid.as<uint32_t>(); }
@@ -1611,11 +1629,11 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         CK(cudaEventSynchronize(ctx->ev_end));      // the kernels are through: the GPU is the next tile's
         gate.unlock();
     }
-    if (!out_dev) {
+    if (!out_dev && !mapped_out) {
         if (want_s) CK(cudaMemcpyAsync(scores, d_scores, n_res * 4, cudaMemcpyDeviceToHost, s0));
         if (want_i) CK(cudaMemcpyAsync(n_identical, d_nid, n_res * 4, cudaMemcpyDeviceToHost, s0));
-        ctx->stats.d2h_bytes += (want_s ? n_res * 4 : 0) + (want_i ? n_res * 4 : 0);
     }
+    if (!out_dev) ctx->stats.d2h_bytes += (want_s ? n_res * 4 : 0) + (want_i ? n_res * 4 : 0);
     CK(cudaStreamSynchronize(s0));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));

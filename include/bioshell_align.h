@@ -84,9 +84,10 @@ bsa_ctx *bsa_create(int device_id);
  * every visible device.  Every entry point below behaves as on a single-device context and
  * returns the same bytes: sequence sets and scoring are replicated to all devices; the library
  * runs one host worker thread per GPU, cuts bsa_align_all_pairs / bsa_all_vs_all /
- * bsa_one_vs_many into one cell-balanced template-range tile per GPU, and each tile's results are
- * copied by its GPU straight into the caller's output buffers at the tile's own t-major offset
- * (true DMA when the buffers come from bsa_host_alloc_pinned).  No collective, no NCCL.
+ * bsa_one_vs_many into one cell-balanced template-range tile per GPU, and each GPU delivers its
+ * tile straight into the caller's output buffers at the tile's own t-major offset (stored by the
+ * kernels themselves when the buffers are page-locked, see bsa_host_alloc_pinned; staged and
+ * copied otherwise).  No collective, no NCCL.
  * (BSA_MULTI_WORKERS_PER_GPU=2: guided tiles pulled from a shared counter, two children per GPU
  * taking turns on it, so that one tile's copy and the next tile's planning overlap the kernels.)
  * Pair-list calls are split into contiguous chunks of equal cells.  BSA_OUT_DEVICE is refused.
@@ -201,7 +202,13 @@ int bsa_local_align_pairs(bsa_ctx *ctx, int q_set, int t_set, const uint32_t *q_
 int bsa_hclust(bsa_ctx *ctx, uint32_t n, const float *dist, int linkage, uint32_t flags,
                uint32_t *mat_i, uint32_t *mat_j, float *merge_dist);
 
-/* Pinned host memory so device->host result copies run at full PCIe rate. */
+/*
+ * Page-locked host memory.  Result buffers of bsa_align_all_pairs / bsa_all_vs_all / bsa_one_vs_many
+ * that are page-locked (from here, or any cudaHostAlloc'd / pinned memory) are written by the kernels
+ * DIRECTLY, 8 bytes per pair over the host link while the alignment runs: no staging copy of the
+ * results in device memory and no device-to-host copy at the end of the call.  Pageable buffers are
+ * staged in device memory and copied when the kernels are through.  Same bytes either way.
+ */
 void *bsa_host_alloc_pinned(size_t bytes);
 void bsa_host_free_pinned(void *p);
 

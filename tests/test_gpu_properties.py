@@ -96,3 +96,24 @@ def test_sharded_ranges_concatenate_to_the_whole(ctx):
         parts = [ctx.align_all_pairs(0, 0, counts, int(b[i]), int(b[i + 1])) for i in range(shards)]
         assert np.array_equal(np.concatenate([p[0] for p in parts]), whole[0])
         assert np.array_equal(np.concatenate([p[1] for p in parts]), whole[1])
+
+
+def test_page_locked_result_buffers_take_direct_stores(ctx):
+    """Results stored by the kernels straight into page-locked caller buffers (no staging, no copy) are the
+    bytes the staged path delivers into pageable buffers -- 32-bit score + identity and 16-bit score only."""
+    import torch
+    res, off = synth.generate(600, seed=21)
+    n = len(off) - 1
+    ctx.set_scoring("BLOSUM62", -10, -1)
+    ctx.load_sequences(0, res, off)
+    s_ref, i_ref = ctx.all_vs_all(0)                       # pageable numpy buffers: staged + copied
+    k = len(s_ref)
+    hs = torch.empty(k, dtype=torch.int32).pin_memory()
+    hi = torch.empty(k, dtype=torch.int32).pin_memory()
+    hs.fill_(-1), hi.fill_(-1)
+    ctx.align_all_pairs(0, 0, np.arange(n, dtype=np.uint32), scores=hs.numpy(), n_identical=hi.numpy().view(np.uint32))
+    assert ctx.stats()["d2h_bytes"] == 8 * k
+    assert np.array_equal(hs.numpy(), s_ref) and np.array_equal(hi.numpy().view(np.uint32), i_ref)
+    hs.fill_(-1)
+    ctx.align_all_pairs(0, 0, np.arange(n, dtype=np.uint32), want_identical=False, scores=hs.numpy())
+    assert np.array_equal(hs.numpy(), s_ref)
