@@ -21,6 +21,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <map>
 #include <vector>
 
 #include "gotoh_kernels.cuh"
@@ -109,6 +110,7 @@ struct bsa_ctx {
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;   // run_pairs_dirs: around the kernels of one batch
     double dirs_kernel_ms = 0.0;                     // ... summed over the batches of the last call
     int wave_attr_smem = -1, trace_attr_set = 0;    // cudaFuncSetAttribute done for these sizes
+    std::map<std::pair<const void*, size_t>, int> occ_cache;   // grid_for: resident CTAs per SM by (kernel, dynamic smem)
     std::mutex* gpu_gate = nullptr;   // child of a multi-device context: one tile's kernels at a time per GPU (planning and copies overlap)
 
     // residue alphabet: one code per distinct raw byte ever loaded; code 0 (kPadCode) is reserved for
@@ -264,9 +266,17 @@ int choose_dirs_k(uint64_t m, int C) {
 // persistent grid for `n_items` items: one wave of resident CTAs at most
 int grid_for(bsa_ctx* ctx, KernelFn fn, int K, int C, uint32_t n_items, uint32_t* grid) {
     const size_t smem = smem_for(K, C);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute and the occupancy of a (kernel, shared-memory size) do not change: asked once per context
+    // (a call launches ~100 kernel groups; on a small problem these runtime calls were a fifth of its wall time)
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, smem));
+    auto it = ctx->occ_cache.find(std::make_pair((const void*)fn, smem));
+    if (it != ctx->occ_cache.end()) {
+        nb = it->second;
+    } else {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, smem));
+        ctx->occ_cache[std::make_pair((const void*)fn, smem)] = nb;
+    }
     if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "kernel does not fit on an SM");
     *grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)nb * ctx->sms);
     return BSA_OK;
