@@ -49,6 +49,9 @@
 #ifndef BSA_TAG2_U_SMALLK
 #define BSA_TAG2_U_SMALLK 0  // aligned two-row blocks with at most this many columns per lane take 8 double steps per iteration (measured with 6 and 10: no gain on cfg2 / one-vs-many, -4..-8 % on 1,000 sequences: off)
 #endif
+#ifndef BSA_TAIL16
+XX
+#endif
 #ifndef BSA_RING
 #define BSA_RING 0          // warp-wide prefetch (measured -0.4 % on cfg2: off) of the boundary column in multi-pass kernels
 #endif
@@ -1188,7 +1191,7 @@ __device__ __forceinline__ ChunkPlan plan_chunks(uint64_t span) {
         p.nbig = (uint32_t)((span + lb - 1) / lb);
         p.nsmall = 0;
     } else {
-        p.head = span - span * 3 / 16;
+        p.head = span - span * BSA_TAIL16 / 16;
         uint64_t lb = p.head / (2 * W);
         lb = lb < kChunkSmall ? kChunkSmall : (lb > kChunkBig ? kChunkBig : lb);
         p.nbig = (uint32_t)((p.head + lb - 1) / lb);
