@@ -50,7 +50,7 @@
 #define BSA_TAG2_U_SMALLK 0  // aligned two-row blocks with at most this many columns per lane take 8 double steps per iteration (measured with 6 and 10: no gain on cfg2 / one-vs-many, -4..-8 % on 1,000 sequences: off)
 #endif
 #ifndef BSA_TAIL16
-XX
+#define BSA_TAIL16 2        // sixteenths of an item's stream that are cut into small chunks, the warps' run-in to the closing barrier (same-box A/B on cfg2: 4 -> 3,425, 3 -> 3,437, 2 -> 3,453, 1 -> 3,451 GCUPS)
 #endif
 #ifndef BSA_RING
 #define BSA_RING 0          // warp-wide prefetch (measured -0.4 % on cfg2: off) of the boundary column in multi-pass kernels
@@ -1175,7 +1175,7 @@ struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= BSA_MB3_MAXK 
 constexpr uint32_t kChunkBig = BSA_CHUNK_BIG;    // stream residues per chunk (pipeline fill is 31 steps)
 constexpr uint32_t kChunkSmall = 640;
 
-// Chunk schedule of one item's stream: big chunks over the first 13/16, small ones over the rest, so the warps
+// Chunk schedule of one item's stream: big chunks over the first 14/16, small ones over the rest, so the warps
 // reach the item's closing barrier within half a small chunk of each other.  The big chunks shrink with the
 // stream so that every warp gets at least two of them, and a short stream (small problems: items of a few
 // thousand residues) is cut into uniform pieces -- with fixed 4,096-residue chunks one warp swept most of such
