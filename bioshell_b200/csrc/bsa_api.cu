@@ -995,7 +995,9 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     // barriers, pipeline fill of short chunks -- are what such a run is made of)
     const char* min_item_env = getenv("BSA_MIN_ITEM_CELLS");        // A/B only
     const double min_item = min_item_env ? atof(min_item_env) : 4194304.0;
-    const double target_cells = std::min(std::max(total_cells / 40000.0, min_item), 268435456.0);
+    const char* n_items_env = getenv("BSA_TARGET_ITEMS");           // A/B only
+    const double n_items_target = n_items_env ? std::max(1000.0, atof(n_items_env)) : 40000.0;
+    const double target_cells = std::min(std::max(total_cells / n_items_target, min_item), 268435456.0);
     struct Group { std::vector<Item> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0, swept = 0; };
     const bool use_tag = !getenv("BSA_NO_TAG");
     std::vector<Fix> fixes;

@@ -1173,7 +1173,10 @@ template <int K>
 struct MinBlocks { static constexpr int value = K <= 4 ? 4 : (K <= BSA_MB3_MAXK ? 3 : 2); };
 
 constexpr uint32_t kChunkBig = BSA_CHUNK_BIG;    // stream residues per chunk (pipeline fill is 31 steps)
-constexpr uint32_t kChunkSmall = 640;
+#ifndef BSA_CHUNK_SMALL
+#define BSA_CHUNK_SMALL 640
+#endif
+constexpr uint32_t kChunkSmall = BSA_CHUNK_SMALL;
 
 // Chunk schedule of one item's stream: big chunks over the first 14/16, small ones over the rest, so the warps
 // reach the item's closing barrier within half a small chunk of each other.  The big chunks shrink with the
