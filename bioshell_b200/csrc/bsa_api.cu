@@ -21,6 +21,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <map>
 #include <vector>
 
@@ -109,8 +110,7 @@ struct bsa_ctx {
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_s[kStreams] = {};
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;   // run_pairs_dirs: around the kernels of one batch
     double dirs_kernel_ms = 0.0;                     // ... summed over the batches of the last call
-    int wave_attr_smem = -1, trace_attr_set = 0;    // cudaFuncSetAttribute done for these sizes
-    std::map<std::pair<const void*, size_t>, int> occ_cache;   // grid_for: resident CTAs per SM by (kernel, dynamic smem)
+    int wave_attr_smem = -1;    // wavefront kernel: occupancy checked for this shared-memory size
     std::mutex* gpu_gate = nullptr;   // child of a multi-device context: one tile's kernels at a time per GPU (planning and copies overlap)
 
     // residue alphabet: one code per distinct raw byte ever loaded; code 0 (kPadCode) is reserved for
@@ -263,19 +263,38 @@ int choose_dirs_k(uint64_t m, int C) {
     return best;   // multi-pass with the largest K that fits
 }
 
+// The dynamic shared-memory limit of a kernel is a property of the (device, function), shared by every context of
+// the process.  Contexts with different alphabets ask for different sizes, so the limit is only ever RAISED
+// (a per-context "already set" flag let a second context lower it under the first one's feet).
+cudaError_t raise_smem_limit(int device, const void* fn, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> limit;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& lim = limit[std::make_pair(device, fn)];
+    if (smem <= lim) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) lim = smem;
+    return e;
+}
+
 // persistent grid for `n_items` items: one wave of resident CTAs at most
 int grid_for(bsa_ctx* ctx, KernelFn fn, int K, int C, uint32_t n_items, uint32_t* grid) {
     const size_t smem = smem_for(K, C);
-    // the attribute and the occupancy of a (kernel, shared-memory size) do not change: asked once per context
-    // (a call launches ~100 kernel groups; on a small problem these runtime calls were a fifth of its wall time)
+    // the limit and the occupancy are asked once per (device, kernel, size) instead of once per launch
+    CK(raise_smem_limit(ctx->device, (const void*)fn, smem));
     int nb = 0;
-    auto it = ctx->occ_cache.find(std::make_pair((const void*)fn, smem));
-    if (it != ctx->occ_cache.end()) {
-        nb = it->second;
-    } else {
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, smem));
-        ctx->occ_cache[std::make_pair((const void*)fn, smem)] = nb;
+    {
+        static std::mutex mu;
+        static std::map<std::tuple<int, const void*, size_t>, int> occ;                  // (device, fn, smem) -> CTAs per SM
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_tuple(ctx->device, (const void*)fn, smem);
+        auto it = occ.find(key);
+        if (it != occ.end()) {
+            nb = it->second;
+        } else {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreads, smem));
+            occ[key] = nb;
+        }
     }
     if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "kernel does not fit on an SM");
     *grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)nb * ctx->sms);
@@ -486,17 +505,14 @@ int run_pairs_dirs(bsa_ctx* ctx, const SeqSet& Q, const SeqSet& T, std::vector<P
         // everything the host has to ask the runtime is asked before the first launch, so that the kernels of the
         // batch run back to back and the two events around them time the device, not the host
         const size_t wave_smem = wave_smem_bytes(wave_warps, C) + 1024;      // + slack to align the rings to 1 KB
+        if (!wave_items.empty()) CK(raise_smem_limit(ctx->device, (const void*)gotoh_wave_kernel, wave_smem));
         if (!wave_items.empty() && ctx->wave_attr_smem != (int)wave_smem) {
-            CK(cudaFuncSetAttribute(gotoh_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
             int nb = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gotoh_wave_kernel, wave_warps * 32, wave_smem));
             if (nb < 1) return fail(ctx, BSA_ERR_CUDA, "wavefront kernel does not fit on an SM");
             ctx->wave_attr_smem = (int)wave_smem;
         }
-        if (!local && !ctx->trace_attr_set) {
-            CK(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTraceWinLong)));
-            ctx->trace_attr_set = 1;
-        }
+        if (!local) CK(raise_smem_limit(ctx->device, (const void*)traceback_kernel, 2 * kTraceWinLong));
         if (!wave_items.empty()) {
             CK(ctx->wave_items.ensure(wave_items.size() * sizeof(uint2)));
             CK(cudaMemcpyAsync(ctx->wave_items.p, wave_items.data(), wave_items.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));

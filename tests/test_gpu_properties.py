@@ -117,3 +117,32 @@ def test_page_locked_result_buffers_take_direct_stores(ctx):
     hs.fill_(-1)
     ctx.align_all_pairs(0, 0, np.arange(n, dtype=np.uint32), want_identical=False, scores=hs.numpy())
     assert np.array_equal(hs.numpy(), s_ref)
+
+
+def test_two_contexts_with_different_alphabets_take_turns():
+    """The dynamic shared-memory limit of a kernel belongs to the (device, function), not to a context: a context
+    with a small alphabet must not lower it under a context with a large one (the library only ever raises it).
+    Streaming kernels and the wavefront kernel, calls alternating between the two contexts."""
+    rng = np.random.default_rng(3)
+    res, off = synth.generate(120, seed=31, dist=0, lo=40, hi=700)
+    wide = res.copy()
+    idx = rng.integers(0, len(wide), 400)
+    wide[idx] = rng.integers(130, 200, 400).astype(np.uint8)        # 70 more byte values: a much larger profile
+    lres, loff = synth.pair_set(1, seed=9, lo=4300, hi=4800)
+    lwide = lres.copy()
+    lwide[rng.integers(0, len(lwide), 50)] = rng.integers(130, 200, 50).astype(np.uint8)
+    with bs.Context(0) as a, bs.Context(0) as b:
+        for c, r, lr in ((a, wide, lwide), (b, res, lres)):
+            c.set_scoring("BLOSUM62", -10, -1)
+            c.load_sequences(0, r, off)
+            c.load_sequences(1, lr, loff)
+        first = {}
+        for rnd in range(2):
+            for name, c in (("a", a), ("b", b)):
+                s, n = c.all_vs_all(0)
+                s2, n2, p2 = c.align_pairs_paths(1, 1, [0], [1])
+                got = (s.tobytes(), n.tobytes(), int(s2[0]), int(n2[0]), bytes(p2[0]))
+                if rnd == 0:
+                    first[name] = got
+                else:
+                    assert got == first[name], name
