@@ -19,7 +19,11 @@
 //    higher score first, then the reference's priority among equal scores
 //    (H: diagonal 3 > E 2 > F 1, global.rs:161-169; E/F: extend beats open,
 //    global.rs:109,122), and the count of identical residues of the winning
-//    path rides along for free.  The whole cell is 8 integer instructions:
+//    path rides along for free.  This CLASSIC cell (templates whose scores leave
+//    no room for a tag field, and the direction-store kernels) is 8 integer
+//    instructions; the score + identity kernels run the TAG cell in the moving
+//    frame score - (i + j) ge instead -- 5 instructions, see kTagBits below and
+//    stream_block_tag2a (two rows per step over the even-aligned stream):
 //        e  = eraw | PH                      LOP3
 //        f  = fraw[c] | PV                   LOP3
 //        d  = hdiag + T[q][t]                IADD3      (T carries prio 3 and the identity bit)
@@ -223,7 +227,11 @@ struct Consts {
 //      opening outranks a newer one, and every kTagRows steps the stored F get the top bit of x
 //      (an OR), which outranks every opening of the next 16 steps.
 // The cell is 6 instructions: IMAD (diagonal), VIMNMX3, LOP3, IMAD (E opening), 2 VIADDMNMX.
-// tests/packed_model.py::frame_align is the scalar model of exactly this arithmetic.
+// In the aligned two-row blocks (stream_block_tag2a, BSA_ETAG) E uses F's scheme along the columns of a
+// lane instead -- the opening of column c carries x = K-1-c, an E that crosses a lane boundary gets the
+// whole field -- so the E update is ONE VIADDMNMX with a warp-uniform per-column constant and the cell is
+// 5 instructions: IMAD (diagonal), VIMNMX3, LOP3, 2 VIADDMNMX.
+// tests/packed_model.py::frame_align is the scalar model of exactly this arithmetic (both E schemes).
 constexpr int kTagBits = 5;
 constexpr uint32_t kTagRows = 16;
 
