@@ -132,7 +132,7 @@ struct bsa_ctx {
     DevBuf items, counters, scratch, out_scores, out_nid, fixes, pairs, dirs, path, pstart, status,
         raw, lut, presence, progress, wave_items, hc_matrix, hc_aux, items16, scratch16, items_pair,
         lt_codes, lt_off, lt_idx, lq_codes, lq_off, lq_idx, lutB, lutC, wave_bnd, gidx,
-        lt_acodes, lt_aoff, lq_acodes, lq_aoff;
+        lt_acodes, lt_aoff, lq_acodes, lq_aoff, items16q;
     bsa_stats stats;
     uint64_t pending_h2d = 0;   // bytes uploaded by bsa_load_sequences since the last alignment call
     uint32_t wave_epoch = 0;    // tag of the last wavefront launch on wave_bnd
@@ -173,6 +173,8 @@ typedef void (*KernelPairFn)(const KArgsPair);
 KernelPairFn g_pair[kKMax + 1], g_pair_tag[kKMax + 1];
 KernelLocalFn g_local[kKMax + 1];
 Kernel16Fn g_score16_single[kKMax + 1], g_score16_multi[kKMax + 1];
+typedef void (*Kernel16QFn)(const KArgs16Q);
+Kernel16QFn g_score16_quad[kKMax + 1];
 
 template <int K>
 struct Reg {
@@ -181,6 +183,7 @@ struct Reg {
         g_stream_multi[K] = gotoh_stream_kernel<K, true>;
         g_score16_single[K] = gotoh_score16_kernel<K, false>;
         g_score16_multi[K] = gotoh_score16_kernel<K, true>;
+        g_score16_quad[K] = gotoh_score16_quad_kernel<K>;
         g_pair[K] = gotoh_pair_kernel<K>;
         g_stream_single_tag[K] = gotoh_stream_kernel<K, false, true>;
         g_stream_multi_tag[K] = gotoh_stream_kernel<K, true, true>;
@@ -717,7 +720,7 @@ void bsa_destroy(bsa_ctx* c) {
                       &c->pairs, &c->dirs, &c->path, &c->pstart, &c->status, &c->raw, &c->lut,
                       &c->presence, &c->d_subst, &c->d_isgap, &c->progress, &c->wave_items, &c->hc_matrix, &c->hc_aux, &c->items16, &c->scratch16, &c->items_pair,
                       &c->lt_codes, &c->lt_off, &c->lt_idx, &c->lq_codes, &c->lq_off, &c->lq_idx, &c->lutB, &c->lutC,
-                      &c->wave_bnd, &c->gidx, &c->lt_acodes, &c->lt_aoff, &c->lq_acodes, &c->lq_aoff};
+                      &c->wave_bnd, &c->gidx, &c->lt_acodes, &c->lt_aoff, &c->lq_acodes, &c->lq_aoff, &c->items16q};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < kStreams; ++i) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
@@ -1025,13 +1028,28 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     struct Group16 { std::vector<Item16> items; uint64_t stride = 0; uint64_t scr_off = 0; double cells = 0; };
     std::vector<Group16> groups16(2 * (kKMax + 1));
     std::vector<uint8_t> done16((size_t)(t_end - t_begin), 0);
+    // short templates (<= 16 x 20 columns): FOUR per warp on two 16-lane pipelines (gotoh_score16_quad_kernel)
+    struct Group16Q { std::vector<Item16Q> items; double cells = 0; };
+    std::vector<Group16Q> groups16Q(kKMax + 1);
     if (want_s && !want_i && Q.empties.empty() && !getenv("BSA_NO_S16")) {
         struct Cand { uint32_t t, cnt; uint64_t m; int key; };
-        std::vector<Cand> cands;
+        std::vector<Cand> cands, qcands;
+        const bool quad_on = BSA_ALIGNED && !getenv("BSA_NO_QUAD16");
         for (uint32_t t = t_begin; t < t_end; ++t) {
             const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
             const uint64_t m = T.len(t);
             if (cnt == 0 || m == 0) continue;
+            if (quad_on && m <= 16ull * kKStream) {
+                const int K16 = (int)((m + 15) / 16);
+                const uint64_t m_pad = 16ull * K16;
+                const int64_t ubq = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_pad, Q.maxlen) +
+                                    (int64_t)(Q.maxlen + m_pad + 8) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+                const int64_t lbq = 4 * (int64_t)(ctx->ge - ctx->go) + 4 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
+                if (std::max(ubq, lbq) < 32000 && smem_for(K16, C) <= kSmemBudget) {
+                    qcands.push_back(Cand{t, cnt, m, K16});
+                    continue;
+                }
+            }
             const KChoice kc = choose_k(m, C);
             if (kc.K < 1) continue;
             // every DP value (incl. borders, E/F one step below them, and the padded columns of the
@@ -1087,6 +1105,43 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             done16[A.t - t_begin] = 1;
             if (B) done16[B->t - t_begin] = 1;
             i += pair ? 2 : 1;
+        }
+        // quads: four templates of the same 16-column class and the same query count per item
+        std::stable_sort(qcands.begin(), qcands.end(), [](const Cand& a, const Cand& b) {
+            if (a.key != b.key) return a.key < b.key;
+            if (a.cnt != b.cnt) return a.cnt < b.cnt;
+            return a.m < b.m;
+        });
+        for (size_t i = 0; i < qcands.size();) {
+            const Cand& A = qcands[i];
+            size_t nq = 1;
+            while (nq < 4 && i + nq < qcands.size() && qcands[i + nq].key == A.key && qcands[i + nq].cnt == A.cnt) ++nq;
+            const int K16 = A.key;
+            const uint64_t m_pad = 16ull * K16;
+            uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
+            xb = std::min<uint64_t>(xb, 1u << 18);
+            double msum = 0;
+            for (size_t k = 0; k < nq; ++k) msum += (double)qcands[i + k].m;
+            uint32_t q = 0;
+            while (q < A.cnt) {
+                const uint64_t lim_off = Q.off[q] + xb;
+                uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + A.cnt + 1, lim_off) -
+                                         Q.off.begin()) - 1;
+                q2 = std::min(std::max(q2, q + 1), A.cnt);
+                Item16Q it;
+                for (size_t k = 0; k < 4; ++k) {
+                    it.t[k] = k < nq ? qcands[i + k].t : 0xffffffffu;
+                    it.out[k] = k < nq ? first[qcands[i + k].t - t_begin] + q : 0;
+                }
+                it.q_begin = q; it.q_end = q2;
+                groups16Q[K16].items.push_back(it);
+                const uint64_t x = Q.off[q2] - Q.off[q];
+                padded += (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad * (double)nq;
+                groups16Q[K16].cells += (double)x * msum;
+                q = q2;
+            }
+            for (size_t k = 0; k < nq; ++k) done16[qcands[i + k].t - t_begin] = 1;
+            i += nq;
         }
     }
 
@@ -1463,12 +1518,13 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
         }
     ctx->stats.items = (uint32_t)(all.size() + all_pair.size());
     constexpr size_t kCounters16 = 1024;     // the 16-bit groups' counters follow those of the launches above
-    CK(ctx->counters.ensure((kCounters16 + groups16.size()) * 4));
+    const size_t n_counters = kCounters16 + groups16.size() + groups16Q.size();
+    CK(ctx->counters.ensure(n_counters * 4));
     if (launches.size() > kCounters16) return fail(ctx, BSA_ERR_CUDA, "too many kernel groups");
     cudaStream_t s0 = ctx->streams[0];
-    CK(cudaMemsetAsync(ctx->counters.p, 0, (kCounters16 + groups16.size()) * 4, s0));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, n_counters * 4, s0));
     // every item list goes up before the start event, so that every stream only has to wait for that one event
-    std::vector<size_t> goff16(groups16.size(), 0);
+    std::vector<size_t> goff16(groups16.size(), 0), goff16Q(groups16Q.size(), 0);
     {
         if (!all.empty()) {
             CK(ctx->items.ensure(all.size() * sizeof(Item)));
@@ -1481,6 +1537,7 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             ctx->stats.h2d_bytes += all_pair.size() * sizeof(Item16);
         }
         std::vector<Item16> all16;
+        std::vector<Item16Q> all16q;
         for (int g = (int)groups16.size() - 1; g >= 0; --g) {
             goff16[g] = all16.size();
             all16.insert(all16.end(), groups16[g].items.begin(), groups16[g].items.end());
@@ -1489,6 +1546,15 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             CK(ctx->items16.ensure(all16.size() * sizeof(Item16)));
             CK(cudaMemcpyAsync(ctx->items16.p, all16.data(), all16.size() * sizeof(Item16), cudaMemcpyHostToDevice, s0));
             ctx->stats.h2d_bytes += all16.size() * sizeof(Item16);
+        }
+        for (int g = (int)groups16Q.size() - 1; g >= 0; --g) {
+            goff16Q[g] = all16q.size();
+            all16q.insert(all16q.end(), groups16Q[g].items.begin(), groups16Q[g].items.end());
+        }
+        if (!all16q.empty()) {
+            CK(ctx->items16q.ensure(all16q.size() * sizeof(Item16Q)));
+            CK(cudaMemcpyAsync(ctx->items16q.p, all16q.data(), all16q.size() * sizeof(Item16Q), cudaMemcpyHostToDevice, s0));
+            ctx->stats.h2d_bytes += all16q.size() * sizeof(Item16Q);
         }
         CK(cudaStreamSynchronize(s0));   // `all16` is a temporary
     }
@@ -1568,6 +1634,45 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                 fprintf(stderr, "[bsa %s %s] K=%2d multi=%d tag=%d items=%7u cells=%.4e swept/cells=%.3f ms=%9.3f GCUPS=%8.1f\n",
                         L.pair ? "pair " : "group", V.name, K, (!L.pair && group_multi(L.g)) ? 1 : 0, tag ? 1 : 0, L.n_items, cells,
                         cells > 0 ? swept / cells : 0.0, ms, ms > 0 ? cells / 1e6 / ms : 0.0);
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+            }
+            ++li;
+        }
+    }
+    // ---- 16-bit score-only quads: four short templates per warp ----
+    {
+        const bool prof_groups = getenv("BSA_PROFILE_GROUPS") != nullptr;
+        int li = 0;
+        for (int g = (int)groups16Q.size() - 1; g >= 1; --g) {
+            Group16Q& G = groups16Q[g];
+            if (G.items.empty()) continue;
+            KArgs16Q a;
+            memset(&a, 0, sizeof(a));
+            a.Q = Q.dev(); a.T = T.dev(); a.QA = Q.adev();
+            a.subst = ctx->d_subst.as<int16_t>();
+            a.C = C; a.go = ctx->go; a.ge = ctx->ge;
+            a.items = ctx->items16q.as<Item16Q>() + goff16Q[g];
+            a.n_items = (uint32_t)G.items.size();
+            a.item_counter = ctx->counters.as<uint32_t>() + kCounters16 + groups16.size() + g;
+            a.scores = d_scores;
+            const size_t smem = smem_for(g, C);
+            uint32_t grid = 0;
+            rc = grid_for(ctx, (KernelFn)g_score16_quad[g], g, C, a.n_items, &grid);
+            if (rc) return rc;
+            cudaStream_t st = prof_groups ? s0 : ctx->streams[(li + 3) % kStreams];
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (prof_groups) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+            g_score16_quad[g]<<<grid, kThreads, smem, st>>>(a);
+            CK(cudaGetLastError());
+            ctx->stats.launches++;
+            ctx->stats.items += a.n_items;
+            if (prof_groups) {
+                cudaEventRecord(e1, st);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                fprintf(stderr, "[bsa quad16] K=%2d items=%7zu cells=%.4e ms=%9.3f GCUPS=%8.1f\n", g, G.items.size(), G.cells, ms,
+                        ms > 0 ? G.cells / 1e6 / ms : 0.0);
                 cudaEventDestroy(e0); cudaEventDestroy(e1);
             }
             ++li;

@@ -250,7 +250,7 @@ __host__ __device__ constexpr size_t smem_bytes(int C) {
     return (size_t)(C + 2) * KTraits<K>::ROW * sizeof(uint4);
 }
 __host__ __device__ constexpr uint32_t subst_stage_bytes(int C) { return ((uint32_t)(C * C * 2) + 15u) & ~15u; }
-__host__ __device__ constexpr uint32_t slice_stage_bytes(int K) { return 32u * (uint32_t)K + 32u; }
+__host__ __device__ constexpr uint32_t slice_stage_bytes(int K) { return 32u * (uint32_t)K + 64u; }   // two of them also hold four 16 K + 32 byte slices (quad kernel)
 __host__ __device__ constexpr size_t stage_bytes(int K, int C) {
     return (size_t)subst_stage_bytes(C) + 2u * slice_stage_bytes(K);
 }
@@ -1728,7 +1728,7 @@ _Pragma("unroll")                                                               
 // the end-of-sequence flag always sits on the second row of a double step and the interleaved
 // two-row body is the only form of the cell code.  Values stay biased by 0x8000 per half.
 // The score leaves the frame when it is emitted: H = H* + (n + m) ge with the sequence's real length.
-template <int K>
+template <int K, bool HALF = false>
 __device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ codes, uint64_t g0, uint64_t g1,
                                                   const uint4* prof, const int lane, const int lastA,
                                                   const int slotA, const int lastB, const int slotB,
@@ -1739,9 +1739,12 @@ __device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ co
     constexpr int ROWB = KTraits<K>::ROW * (int)sizeof(uint4);
     constexpr int U = K <= BSA_TAG2_U_SMALLK ? 8 : BSA_TAG2_U;
     const uint32_t X = (uint32_t)(g1 - g0);        // even
-    const int span = lastA > lastB ? lastA : lastB;
+    // HALF (gotoh_score16_quad_kernel): lanes 0-15 and 16-31 are two independent 16-lane pipelines (four templates
+    // per warp); lastA/lastB, the template lengths and the output bases are then per-lane values
+    const int span = HALF ? 15 : (lastA > lastB ? lastA : lastB);
     const uint32_t nd = (X / 2u + (uint32_t)span + (U - 1)) / U * U;
-    const bool lane0 = lane == 0;
+    const int lrel = HALF ? (lane & 15) : lane;
+    const bool lane0 = lrel == 0;
     const uint32_t FB = add2(HB, GOF2);            // eager E*[i][1] and F*[1][j]: opened from the border
     // the constant left border enters lane 0 through one LOP3 per value: (shuffled & keep) | border
     const uint32_t keep = (uint32_t)opaque_reg(lane0 ? 0 : -1);
@@ -1756,7 +1759,7 @@ __device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ co
     uint32_t hdiag = hdiag0;
     uint32_t oh0 = 0, oe0 = 0, oh1 = 0, oe1 = 0, emitted = 0;
     const char* prof_lane = reinterpret_cast<const char*>(prof + lane);
-    const uint8_t* p = codes + g0 - 2 * lane;
+    const uint8_t* p = codes + g0 - 2 * lrel;
     uint32_t b[2 * U], nb[2 * U];
 #pragma unroll
     for (int u = 0; u < 2 * U; ++u) b[u] = ld_code(p + u);
@@ -1805,7 +1808,7 @@ __device__ __forceinline__ void stream_block16_fa(const uint8_t* __restrict__ co
             oh1 = h1;
             oe1 = e1;
             if (b1 & kLastFlag) {
-                const uint32_t pos1 = 2u * (S + u - (uint32_t)lane) + 1u;   // wraps below row 0: fails pos1 < X
+                const uint32_t pos1 = 2u * (S + u - (uint32_t)lrel) + 1u;   // wraps below row 0: fails pos1 < X
                 const bool valid = pos1 < X;
                 if (valid && scores && (lane == lastA || lane == lastB)) {
                     const int n = (int)(qoffp[emitted + 1] - qoffp[emitted]);
@@ -2115,6 +2118,135 @@ __global__ void __launch_bounds__(kThreads, MinBlocks16<K, MULTI>::value) gotoh_
                                              GO32, a.one, MULTI ? scratch + (g0 - x0) : nullptr, a.scores,
                                              it.outA + (qa - it.q_begin), it.outB + (qa - it.q_begin));
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Score only, FOUR short templates per warp (templates of at most 16 K <= 320 columns): lanes 0-15 carry
+// templates A (low halves) and B (high halves), lanes 16-31 templates C and D, all four fed by the same
+// stream (stream_block16_fa<K, HALF>: two independent 16-lane pipelines, lane 16 takes the left border
+// instead of lane 15's shuffle).  Each lane then owns twice as many columns as with two templates per warp,
+// so the per-step bookkeeping is paid once per 4 K cells, the column padding drops to 16 columns and the
+// pipeline fill to 15 double steps.  Moving frame, even-aligned stream, PAD rows as in the two-template kernel.
+struct Item16Q {
+    uint32_t t[4];          // 0xffffffff: no template in this slot (A is always present)
+    uint32_t q_begin, q_end;
+    uint64_t out[4];        // result index of (q_begin, t[i])
+};
+struct KArgs16Q {
+    SeqStoreDev Q, T, QA;
+    const int16_t* subst;
+    int C, go, ge;
+    const Item16Q* items;
+    uint32_t n_items;
+    uint32_t* item_counter;
+    int32_t* scores;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, MinBlocks16<K, false>::value) gotoh_score16_quad_kernel(const KArgs16Q a) {
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_chunk;
+    constexpr int ROW = KTraits<K>::ROW;
+    uint4* prof = smem;
+    uint4* rsH = smem + (size_t)a.C * ROW;      // (border vectors unused: the frame's borders are constants)
+    uint4* rsF = rsH + ROW;
+    const int lane = threadIdx.x & 31;
+    const int lrel = lane & 15;
+    const int half = lane >> 4;
+    BSA_TMA_PREAMBLE(K, a.C, a.subst)
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t ii = s_item;
+        if (ii >= a.n_items) break;
+        const Item16Q it = a.items[ii];
+        uint64_t t0[4];
+        uint32_t m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool has = it.t[i] != 0xffffffffu;
+            t0[i] = has ? a.T.off[it.t[i]] : 0;
+            m[i] = has ? (uint32_t)(a.T.off[it.t[i] + 1] - t0[i]) : 0u;
+        }
+        const uint64_t* __restrict__ xoff = a.QA.off;
+        const uint64_t x0 = xoff[it.q_begin], x1 = xoff[it.q_end];
+        const uint64_t span = x1 - x0;
+        const ChunkPlan cp = plan_chunks(span);
+        const uint64_t head = cp.head;
+        const uint32_t nbig = cp.nbig, nsmall = cp.nsmall;
+        const uint32_t nch = nbig + nsmall;
+
+        __syncthreads();
+        BSA_TMA_PTRS(K, a.C)
+        uint8_t* s_tc[4] = {s_tcA, s_tcA + (16 * K + 32), s_tcA + 2 * (16 * K + 32), s_tcA + 3 * (16 * K + 32)};
+        (void)s_tcB;
+        if (threadIdx.x == 0) {
+            s_chunk = 0;
+            uint32_t nb[4], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { nb[i] = m[i] ? slice_bytes(a.T.codes + t0[i], 0, m[i]) : 0u; tot += nb[i]; }
+            TmaStage::arm(&s_mbar, tot);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (nb[i]) TmaStage::copy(&s_mbar, s_tc[i], slice_src(a.T.codes + t0[i], 0), nb[i]);
+        }
+        TmaStage::wait(&s_mbar, s_phase);
+        const uint8_t* v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = slice_view(s_tc[i], a.T.codes + t0[i], 0);
+        // packed profile: lanes 0-15 templates A | B << 16, lanes 16-31 templates C | D << 16; frame values
+        for (int idx = threadIdx.x; idx < a.C * ROW; idx += blockDim.x) {
+            const int code = idx / ROW, r = idx - code * ROW, vv = r >> 5, ln = r & 31;
+            const int h2 = (ln >> 4) * 2;
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * vv + e;
+                const uint32_t col = (uint32_t)(ln & 15) * K + c;
+                const int padv = col == 0 ? a.go - a.ge : 0;
+                int sv[2];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int ti = h2 + hh;
+                    int x = 0;
+                    if (c < K && col < m[ti]) {
+                        const int tcode = v[ti][col] & kCodeMask;
+                        x = code == (int)kPadCode ? padv : (int)s_subst[code * a.C + tcode] - 2 * a.ge;
+                    }
+                    sv[hh] = x;
+                }
+                o[e] = ((uint32_t)sv[0] & 0xffffu) | ((uint32_t)sv[1] << 16);
+                if (BSA_PADSLOT && K % 4 != 0 && c == K)
+                    o[e] = (ln & 15) == 0 ? (code == (int)kPadCode ? kBias2 : pack2b(a.go - a.ge)) : 0u;
+            }
+            prof[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+        BSA_TMA_FLIP()
+        // this lane's two templates (low / high half)
+        const uint32_t mLo = half ? m[2] : m[0], mHi = half ? m[3] : m[1];
+        const uint64_t outLo = half ? it.out[2] : it.out[0], outHi = half ? it.out[3] : it.out[1];
+        const int lastLo = mLo ? (int)((mLo - 1) / K) + 16 * half : -1, slotLo = mLo ? (int)((mLo - 1) % K) : 0;
+        const int lastHi = mHi ? (int)((mHi - 1) / K) + 16 * half : -1, slotHi = mHi ? (int)((mHi - 1) % K) : 0;
+        const uint32_t hdiag0 = lrel == 0 ? kBias2 : pack2b(a.go - a.ge);
+        for (;;) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(&s_chunk, 1u);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= nch) break;
+            const uint64_t ca = c <= nbig ? head * c / nbig : head + (span - head) * (c - nbig) / nsmall;
+            const uint64_t cb = c + 1 <= nbig ? head * (c + 1) / nbig : head + (span - head) * (c + 1 - nbig) / nsmall;
+            const uint32_t qa = c == 0 ? it.q_begin : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + ca);
+            const uint32_t qb = c + 1 == nch ? it.q_end : lower_bound_off(xoff, it.q_begin, it.q_end, x0 + cb);
+            const uint64_t g0 = xoff[qa], g1 = xoff[qb];
+            if (g1 <= g0) continue;
+            stream_block16_fa<K, true>(a.QA.codes, g0, g1, prof, lane, lastLo, slotLo, lastHi, slotHi, hdiag0,
+                                       pack2b(a.go - a.ge), pack2(a.go - a.ge), a.ge, (int)mLo, (int)mHi, a.scores,
+                                       outLo + (qa - it.q_begin), outHi + (qa - it.q_begin), a.Q.off + qa);
         }
     }
 }
