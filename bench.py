@@ -68,7 +68,7 @@ ROOF = {
 # captures committed under profiles/ (quoted, not re-measured per run: counters need a profiler)
 TRAFFIC_QUOTED = {
     "tag": dict(bytes=3194112, source="profiles/r2_ncu_summary_k1_aligned.md: gotoh_stream_kernel<17,single,TAG>, 41.8 ms launch of the cfg2 run"),
-    "s16": dict(bytes=936448, source="profiles/r2_ncu_summary_k1s_frame.md: gotoh_score16_kernel<16,single>, 9.2 ms launch of a 1000 x 20000 run"),
+    "s16": dict(bytes=1360128, source="profiles/r2_ncu_summary_k1s_frame.md: gotoh_score16_quad_kernel<15>, 22.1 ms launch of a 1000 x 50000 run"),
     "dirs": dict(bytes=4381725952, source="profiles/r2_ncu_summary_wave_frame.md: gotoh_wave_kernel on cfg5, 4.20 GB of directions written + 0.18 GB read"),
 }
 
