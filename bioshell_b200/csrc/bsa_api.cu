@@ -1032,13 +1032,36 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
     struct Group16Q { std::vector<Item16Q> items; double cells = 0; };
     std::vector<Group16Q> groups16Q(kKMax + 1);
     if (want_s && !want_i && Q.empties.empty() && !getenv("BSA_NO_S16")) {
-        struct Cand { uint32_t t, cnt; uint64_t m; int key; };
+        struct Cand { uint32_t t, cnt; uint64_t m; int key; int pkey; };     // pkey: key of the two-per-warp path, -1 = not eligible
         std::vector<Cand> cands, qcands;
         const bool quad_on = BSA_ALIGNED && !getenv("BSA_NO_QUAD16");
         for (uint32_t t = t_begin; t < t_end; ++t) {
             const uint32_t cnt = q_counts ? q_counts[t] : Q.n;
             const uint64_t m = T.len(t);
             if (cnt == 0 || m == 0) continue;
+            // two templates per warp (32 lanes, gotoh_score16_kernel)
+            int pkey = -1;
+            const KChoice kc = choose_k(m, C);
+            if (kc.K >= 1) {
+                // every DP value (incl. borders, E/F one step below them, and the padded columns of the
+                // shorter template of a pair) must fit a 16-bit lane; the biased low half must also stay
+                // >= |go| so that the 32-bit `h + GO` never borrows from the high half
+                const uint64_t m_pad16 = 32ull * kc.K * kc.npass;
+                const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_pad16, Q.maxlen);
+                const int64_t lb = 5 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_pad16 + 68) * (int64_t)(-ctx->ge) +
+                                   (int64_t)std::max(-ctx->min_m, 0);
+                bool ok;
+                if (BSA_ALIGNED && !kc.multi) {
+                    // single-block templates run in the moving frame score - (i + j) ge (stream_block16_fa): the frame
+                    // adds up to (n + m) |ge| at the top; at the bottom nothing falls below three openings under a
+                    // substitution score
+                    const int64_t ubf = ub + (int64_t)(Q.maxlen + m_pad16 + 8) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
+                    const int64_t lbf = 4 * (int64_t)(ctx->ge - ctx->go) + 4 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
+                    ok = std::max(ubf, lbf) < 32000;
+                } else ok = std::max(ub, lb) < 32000;
+                if (ok) pkey = kc.K + (kc.multi ? kKMax + 1 : 0) + (int)kc.npass * 256;
+            }
+            // four short templates per warp (two 16-lane pipelines, gotoh_score16_quad_kernel)
             if (quad_on && m <= 16ull * kKStream) {
                 const int K16 = (int)((m + 15) / 16);
                 const uint64_t m_pad = 16ull * K16;
@@ -1046,28 +1069,56 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
                                     (int64_t)(Q.maxlen + m_pad + 8) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
                 const int64_t lbq = 4 * (int64_t)(ctx->ge - ctx->go) + 4 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
                 if (std::max(ubq, lbq) < 32000 && smem_for(K16, C) <= kSmemBudget) {
-                    qcands.push_back(Cand{t, cnt, m, K16});
+                    qcands.push_back(Cand{t, cnt, m, K16, pkey});
                     continue;
                 }
             }
-            const KChoice kc = choose_k(m, C);
-            if (kc.K < 1) continue;
-            // every DP value (incl. borders, E/F one step below them, and the padded columns of the
-            // shorter template of a pair) must fit a 16-bit lane; the biased low half must also stay
-            // >= |go| so that the 32-bit `h + GO` never borrows from the high half
-            const uint64_t m_pad16 = 32ull * kc.K * kc.npass;
-            const int64_t ub = (int64_t)std::max(ctx->max_m, 0) * (int64_t)std::min<uint64_t>(m_pad16, Q.maxlen);
-            const int64_t lb = 5 * (int64_t)(-ctx->go) + (int64_t)(Q.maxlen + m_pad16 + 68) * (int64_t)(-ctx->ge) +
-                               (int64_t)std::max(-ctx->min_m, 0);
-            if (BSA_ALIGNED && !kc.multi) {
-                // single-block templates run in the moving frame score - (i + j) ge (stream_block16_fa): the frame
-                // adds up to (n + m) |ge| at the top; at the bottom nothing falls below three openings under a
-                // substitution score
-                const int64_t ubf = ub + (int64_t)(Q.maxlen + m_pad16 + 8) * (int64_t)(-ctx->ge) + (int64_t)std::max(ctx->max_m, 0);
-                const int64_t lbf = 4 * (int64_t)(ctx->ge - ctx->go) + 4 * (int64_t)(-ctx->ge) + (int64_t)std::max(-ctx->min_m, 0);
-                if (std::max(ubf, lbf) >= 32000) continue;
-            } else if (std::max(ub, lb) >= 32000) continue;
-            cands.push_back(Cand{t, cnt, m, kc.K + (kc.multi ? kKMax + 1 : 0) + (int)kc.npass * 256});
+            if (pkey >= 0) cands.push_back(Cand{t, cnt, m, pkey, pkey});
+        }
+        // quads: templates of the same 16-column class and the same query count, four (or the last three) per item;
+        // what is left over -- one or two of a kind, e.g. every template of a triangle, whose query counts all
+        // differ -- goes two (or one) per warp as before
+        std::stable_sort(qcands.begin(), qcands.end(), [](const Cand& a, const Cand& b) {
+            if (a.key != b.key) return a.key < b.key;
+            if (a.cnt != b.cnt) return a.cnt < b.cnt;
+            return a.m < b.m;
+        });
+        for (size_t i = 0; i < qcands.size();) {
+            const Cand& A = qcands[i];
+            size_t nq = 1;
+            while (nq < 4 && i + nq < qcands.size() && qcands[i + nq].key == A.key && qcands[i + nq].cnt == A.cnt) ++nq;
+            if (nq < 3) {
+                for (size_t k = 0; k < nq; ++k)
+                    if (qcands[i + k].pkey >= 0) { Cand c = qcands[i + k]; c.key = c.pkey; cands.push_back(c); }
+                i += nq;
+                continue;
+            }
+            const int K16 = A.key;
+            const uint64_t m_pad = 16ull * K16;
+            uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
+            xb = std::min<uint64_t>(xb, 1u << 18);
+            double msum = 0;
+            for (size_t k = 0; k < nq; ++k) msum += (double)qcands[i + k].m;
+            uint32_t q = 0;
+            while (q < A.cnt) {
+                const uint64_t lim_off = Q.off[q] + xb;
+                uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + A.cnt + 1, lim_off) -
+                                         Q.off.begin()) - 1;
+                q2 = std::min(std::max(q2, q + 1), A.cnt);
+                Item16Q it;
+                for (size_t k = 0; k < 4; ++k) {
+                    it.t[k] = k < nq ? qcands[i + k].t : 0xffffffffu;
+                    it.out[k] = k < nq ? first[qcands[i + k].t - t_begin] + q : 0;
+                }
+                it.q_begin = q; it.q_end = q2;
+                groups16Q[K16].items.push_back(it);
+                const uint64_t x = Q.off[q2] - Q.off[q];
+                padded += (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad * (double)nq;
+                groups16Q[K16].cells += (double)x * msum;
+                q = q2;
+            }
+            for (size_t k = 0; k < nq; ++k) done16[qcands[i + k].t - t_begin] = 1;
+            i += nq;
         }
         // partners must agree on columns per lane, number of column blocks and query count
         std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
@@ -1105,43 +1156,6 @@ int bsa_align_all_pairs(bsa_ctx* ctx, int q_set, int t_set, const uint32_t* q_co
             done16[A.t - t_begin] = 1;
             if (B) done16[B->t - t_begin] = 1;
             i += pair ? 2 : 1;
-        }
-        // quads: four templates of the same 16-column class and the same query count per item
-        std::stable_sort(qcands.begin(), qcands.end(), [](const Cand& a, const Cand& b) {
-            if (a.key != b.key) return a.key < b.key;
-            if (a.cnt != b.cnt) return a.cnt < b.cnt;
-            return a.m < b.m;
-        });
-        for (size_t i = 0; i < qcands.size();) {
-            const Cand& A = qcands[i];
-            size_t nq = 1;
-            while (nq < 4 && i + nq < qcands.size() && qcands[i + nq].key == A.key && qcands[i + nq].cnt == A.cnt) ++nq;
-            const int K16 = A.key;
-            const uint64_t m_pad = 16ull * K16;
-            uint64_t xb = (uint64_t)std::max(1.0, target_cells / (double)m_pad);
-            xb = std::min<uint64_t>(xb, 1u << 18);
-            double msum = 0;
-            for (size_t k = 0; k < nq; ++k) msum += (double)qcands[i + k].m;
-            uint32_t q = 0;
-            while (q < A.cnt) {
-                const uint64_t lim_off = Q.off[q] + xb;
-                uint32_t q2 = (uint32_t)(std::upper_bound(Q.off.begin() + q + 1, Q.off.begin() + A.cnt + 1, lim_off) -
-                                         Q.off.begin()) - 1;
-                q2 = std::min(std::max(q2, q + 1), A.cnt);
-                Item16Q it;
-                for (size_t k = 0; k < 4; ++k) {
-                    it.t[k] = k < nq ? qcands[i + k].t : 0xffffffffu;
-                    it.out[k] = k < nq ? first[qcands[i + k].t - t_begin] + q : 0;
-                }
-                it.q_begin = q; it.q_end = q2;
-                groups16Q[K16].items.push_back(it);
-                const uint64_t x = Q.off[q2] - Q.off[q];
-                padded += (double)(x + 15.0 * std::max<double>(kWarpsPerCta, (double)x / 3072.0)) * (double)m_pad * (double)nq;
-                groups16Q[K16].cells += (double)x * msum;
-                q = q2;
-            }
-            for (size_t k = 0; k < nq; ++k) done16[qcands[i + k].t - t_begin] = 1;
-            i += nq;
         }
     }
 
